@@ -1,0 +1,419 @@
+// tcgen05 tensor-core implementation of shgan_conv_igemm: the convolution hot path of the SH-GAN
+// generator (replaces cuDNN conv / conv_transpose reached from conv2d_resample.py:26-51 and the
+// per-sample weight materialisation of stylegan.py:149-190).
+//
+// Im2col-free implicit GEMM, one CTA per SM, persistent over output tiles:
+//   D[128 pixels, BN out-channels] += A_tap[128 pixels, 64 ch] * W_tap[BN, 64 ch]^T   for every tap and 64-ch slab
+// * A_tap is fetched straight from the NHWC split planes by a 4-D TMA box {64 ch, TW, TH, TN} whose
+//   (x,y) origin is shifted by the tap offset; out-of-image pixels are zero-filled by the TMA unit, which
+//   is the convolution's zero padding.  The box lands in shared memory as 128 rows of 128 B in the
+//   SWIZZLE_128B K-major layout that tcgen05.mma consumes directly -- no im2col buffer, no register staging.
+// * W_tap is a 2-D TMA box {64 ch, BN} of the pre-packed [tap, Co, C] fp16 weights, same layout.
+// * fp32-class accuracy on fp16 tensor cores: activations and weights are held as fp16 hi+lo pairs
+//   and each slab issues hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator (the dropped lo*lo
+//   term is < 2^-22 relative).  passes == 1 issues hi*hi only.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+//   warps 2-5 = epilogue (tcgen05.ld 32 lanes x 32 columns per instruction -> registers -> fused
+//   demod / noise / bias / lrelu / clamp / skip-add / torgb / next-layer modulation -> split planes).
+//   Two TMEM accumulators (2*BN columns) let the epilogue of tile i overlap the MMAs of tile i+1;
+//   an mbarrier ring of STAGES smem slots decouples TMA from MMA.
+#include "conv_common.cuh"
+
+namespace shgan {
+
+struct ConvTmaps {
+    CUtensorMap a_hi[SHGAN_MAX_SRC];
+    CUtensorMap a_lo[SHGAN_MAX_SRC];
+    CUtensorMap w_hi;
+    CUtensorMap w_lo;
+};
+
+struct TileInfo {
+    int tw_log2, th_log2;       // tile = TN images x TH rows x TW cols = 128 pixels
+    int TW, TH, TN;
+    int tiles_x, tiles_y, tiles_n, nblk;
+    int total;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_M = 128;       // output pixels per tile == UMMA M
+constexpr int TC_KC = 64;       // channels per K slab (= 128 B of fp16 = one swizzle row)
+constexpr int A_BYTES = TC_M * TC_KC * 2;
+
+template <int BN> struct TcCfg {
+    static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int B_BYTES = BN * TC_KC * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN;   // power of two >= 32
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (launch error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("shgan conv_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major, set to 1),
+// SBO >> 4 in [32,46) = 1024 B between 8-row groups, version 1 in [46,48), layout type 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, issued by one thread for the CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on `bar` once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- kernel -------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const EpiParams epi, const TileInfo ti,
+               const int passes) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES] TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES] MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2] MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kslabs = g.C / TC_KC;
+    const int kiters = g.ntaps * kslabs;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < g.num_src; ++s) {
+            prefetch_tmap(&maps.a_hi[s]);
+            prefetch_tmap(&maps.a_lo[s]);
+        }
+        prefetch_tmap(&maps.w_hi);
+        prefetch_tmap(&maps.w_lo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)Cfg::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (passes == 3 ? 2u : 1u) * (uint32_t)(A_BYTES + Cfg::B_BYTES);
+            for (int tile = blockIdx.x; tile < ti.total; tile += gridDim.x) {
+                int m = tile / ti.nblk;
+                const int nb = tile - m * ti.nblk;
+                const int x0 = (m % ti.tiles_x) * ti.TW;
+                m /= ti.tiles_x;
+                const int y0 = (m % ti.tiles_y) * ti.TH;
+                const int n0 = (m / ti.tiles_y) * ti.TN;
+                for (int t = 0; t < g.ntaps; ++t) {
+                    const int s = g.tap_src[t];
+                    const int cx = x0 + g.tap_dx[t], cy = y0 + g.tap_dy[t];
+                    const int wrow = g.tap_w[t] * g.Co + nb * BN;
+                    for (int ks = 0; ks < kslabs; ++ks) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        tma_load_4d(sa, &maps.a_hi[s], &full_bar[stage], ks * TC_KC, cx, cy, n0);
+                        tma_load_2d(sa + 2 * A_BYTES, &maps.w_hi, &full_bar[stage], ks * TC_KC, wrow);
+                        if (passes == 3) {
+                            tma_load_4d(sa + A_BYTES, &maps.a_lo[s], &full_bar[stage], ks * TC_KC, cx, cy, n0);
+                            tma_load_2d(sa + 2 * A_BYTES + Cfg::B_BYTES, &maps.w_lo, &full_bar[stage], ks * TC_KC, wrow);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A/B fp16 (0), both K-major,
+            // N>>3 in [17,23), M>>4 in [24,29)
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < ti.total; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int it = 0; it < kiters; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_KC / 16; ++k) {
+                        const uint32_t ko = k * 32;  // 16 fp16 = 32 B inside the 128 B swizzle row
+                        const uint64_t dah = umma_desc_sw128(a_hi + ko), dbh = umma_desc_sw128(b_hi + ko);
+                        umma_f16(d_tmem, dah, dbh, idesc, (it | k) != 0);
+                        if (passes == 3) {
+                            umma_f16(d_tmem, umma_desc_sw128(a_lo + ko), dbh, idesc, 1);
+                            umma_f16(d_tmem, dah, umma_desc_sw128(b_lo + ko), idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
+        const int tx_i = row & (ti.TW - 1);
+        const int ty_i = (row >> ti.tw_log2) & (ti.TH - 1);
+        const int tn_i = row >> (ti.tw_log2 + ti.th_log2);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < ti.total; tile += gridDim.x) {
+            int m = tile / ti.nblk;
+            const int nb = tile - m * ti.nblk;
+            const int x = (m % ti.tiles_x) * ti.TW + tx_i;
+            m /= ti.tiles_x;
+            const int y = (m % ti.tiles_y) * ti.TH + ty_i;
+            const int n = (m / ti.tiles_y) * ti.TN + tn_i;
+            const bool valid = n < g.N && y < g.OH && x < g.OW;
+            const long long pix = ((long long)n * g.OH + y) * g.OW + x;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                if (valid) {
+                    const int o0 = nb * BN + c0;
+                    if (g.mode == 1) raw_store<32>(g, v, n, y, x, o0);
+                    else epilogue_apply<32>(epi, v, n, y, x, g.OH, g.OW, g.Co, o0, rgb, pix);
+                }
+            }
+            if (valid && g.mode == 0 && epi.rgb_w) {
+                float* dst = epi.rgb_out + (pix * ti.nblk + nb) * 4;
+                *reinterpret_cast<float4*>(dst) = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    SHGAN_CHECK(fn, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bdim[4], estr[4];
+    uint64_t stride = 2;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstr[i] = stride;
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SHGAN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
+static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+template <int BN>
+static int launch_bn(const ConvTmaps& maps, const ConvGeom& g, const EpiParams& epi, const TileInfo& ti, int passes,
+                     cudaStream_t stream) {
+    using Cfg = TcCfg<BN>;
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
+        SHGAN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        int dev = 0;
+        SHGAN_CUDA(cudaGetDevice(&dev));
+        SHGAN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    const int grid = ti.total < num_sms ? ti.total : num_sms;
+    conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, g, epi, ti, passes);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream) {
+    SHGAN_CHECK(g.C % TC_KC == 0, "C must be a multiple of 64 for the tensor-core path");
+    SHGAN_CHECK(block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 64, 128 or 256");
+    SHGAN_CHECK(g.Co % block_n == 0, "Co must be a multiple of block_n");
+    SHGAN_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
+    TileInfo ti;
+    ti.TW = pow2_ceil(g.OW) < 16 ? pow2_ceil(g.OW) : 16;
+    const int th_max = TC_M / ti.TW;
+    ti.TH = pow2_ceil(g.OH) < th_max ? pow2_ceil(g.OH) : th_max;
+    ti.TN = TC_M / (ti.TW * ti.TH);
+    ti.tw_log2 = ilog2(ti.TW);
+    ti.th_log2 = ilog2(ti.TH);
+    ti.tiles_x = ceil_div(g.OW, ti.TW);
+    ti.tiles_y = ceil_div(g.OH, ti.TH);
+    ti.tiles_n = ceil_div(g.N, ti.TN);
+    ti.nblk = g.Co / block_n;
+    const long long total = (long long)ti.tiles_x * ti.tiles_y * ti.tiles_n * ti.nblk;
+    SHGAN_CHECK(total <= INT32_MAX, "too many tiles");
+    ti.total = (int)total;
+
+    ConvTmaps maps;
+    const uint32_t abox[4] = {(uint32_t)TC_KC, (uint32_t)ti.TW, (uint32_t)ti.TH, (uint32_t)ti.TN};
+    for (int s = 0; s < g.num_src; ++s) {
+        const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.src_w[s], (uint64_t)g.src_h[s], (uint64_t)g.N};
+        if (int e = encode_map(&maps.a_hi[s], g.src_hi[s], 4, dims, abox)) return e;
+        if (int e = encode_map(&maps.a_lo[s], g.src_lo[s], 4, dims, abox)) return e;
+    }
+    int w_taps = 0;
+    for (int t = 0; t < g.ntaps; ++t) w_taps = g.tap_w[t] + 1 > w_taps ? g.tap_w[t] + 1 : w_taps;
+    // the caller-declared w_taps bounds the map; use the larger of the two so a bad tap index cannot read past it
+    const uint64_t wdims[2] = {(uint64_t)g.C, (uint64_t)w_taps * g.Co};
+    const uint32_t wbox[2] = {(uint32_t)TC_KC, (uint32_t)block_n};
+    if (int e = encode_map(&maps.w_hi, g.w_hi, 2, wdims, wbox)) return e;
+    if (int e = encode_map(&maps.w_lo, g.w_lo, 2, wdims, wbox)) return e;
+
+    if (block_n == 64) return launch_bn<64>(maps, g, epi, ti, passes, stream);
+    if (block_n == 128) return launch_bn<128>(maps, g, epi, ti, passes, stream);
+    return launch_bn<256>(maps, g, epi, ti, passes, stream);
+}
+
+}  // namespace shgan

@@ -1,0 +1,161 @@
+// Fully-connected layers and style preparation (sm_100a).
+//
+// Batch sizes on this path are tiny (B <= 32 per GPU), so every dense layer is a weight-streaming
+// GEMV-like problem bounded by reading W once from HBM: one warp owns one output feature, streams
+// its weight row with 128-bit loads and keeps up to 8 batch accumulators in registers; the input
+// rows (a few hundred KB at most) are served by L1/L2.
+//   shgan_dense_fwd            <- dense.forward (torch.addmm), lib/model_zoo/stylegan.py:87-98
+//   shgan_normalize_2nd_moment <- normalize_2nd_moment, stylegan.py:343-344
+//   shgan_style_prep           <- the style / demodulation arithmetic of modulated_conv2d, stylegan.py:145-155
+#include "common.cuh"
+
+namespace shgan {
+
+constexpr int DB = 8;  // batch rows per pass
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+dense_kernel(const float* __restrict__ x0, long long x0_stride, int I0, const float* __restrict__ x1, long long x1_stride,
+             const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y, long long y_stride, int B,
+             int I, int O, float wgain, float bgain, int act, float act_alpha, float act_gain, float act_clamp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + warp;
+    if (o >= O) return;
+    const float* wr = w + (long long)o * I;
+    for (int b0 = 0; b0 < B; b0 += DB) {
+        float acc[DB];
+#pragma unroll
+        for (int j = 0; j < DB; ++j) acc[j] = 0.f;
+        for (int i = lane * 4; i < I; i += 128) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + i));
+            const bool first = i < I0;  // I0 is a multiple of 4, so a quad never straddles the two inputs
+#pragma unroll
+            for (int j = 0; j < DB; ++j) {
+                if (b0 + j < B) {
+                    const float* xp = first ? x0 + (long long)(b0 + j) * x0_stride + i
+                                            : x1 + (long long)(b0 + j) * x1_stride + (i - I0);
+                    const float4 xv = __ldg(reinterpret_cast<const float4*>(xp));
+                    acc[j] = fmaf(xv.x, wv.x, acc[j]);
+                    acc[j] = fmaf(xv.y, wv.y, acc[j]);
+                    acc[j] = fmaf(xv.z, wv.z, acc[j]);
+                    acc[j] = fmaf(xv.w, wv.w, acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DB; ++j) acc[j] = warp_sum(acc[j]);
+        if (lane == 0) {
+            const float bv = bias ? __ldg(bias + o) * bgain : 0.f;
+#pragma unroll
+            for (int j = 0; j < DB; ++j) {
+                if (b0 + j < B) {
+                    float v = acc[j] * wgain + bv;
+                    if (act) v = lrelu_agc(v, act_alpha, act_gain, act_clamp);
+                    y[(long long)(b0 + j) * y_stride + o] = v;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+normalize_2nd_moment_kernel(const float* __restrict__ z, float* __restrict__ y, int D) {
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float v = z[(long long)b * D + i];
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float sc = rsqrtf(tot / (float)D + 1e-8f);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) y[(long long)b * D + i] = z[(long long)b * D + i] * sc;
+}
+
+// one block: s_hat = s * (demod ? rsqrt(mean over the WHOLE [N,Ci] tensor of s^2) : pre_scale)
+__global__ void __launch_bounds__(1024)
+style_scale_kernel(const float* __restrict__ styles, float* __restrict__ s_hat, int total, int demod, float pre_scale) {
+    __shared__ float red[32];
+    float sc = pre_scale;
+    if (demod) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const float v = styles[i];
+            s = fmaf(v, v, s);
+        }
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        float tot = 0.f;
+        for (int i = 0; i < 32; ++i) tot += red[i];
+        sc = rsqrtf(tot / (float)total);
+    }
+    for (int i = threadIdx.x; i < total; i += blockDim.x) s_hat[i] = styles[i] * sc;
+}
+
+// dcoef[n,o] = rsqrt(sum_i s_hat[n,i]^2 * wsq[o,i] + 1e-8); one warp per (n,o)
+__global__ void __launch_bounds__(256)
+dcoef_kernel(const float* __restrict__ s_hat, const float* __restrict__ wsq, float* __restrict__ dcoef, int N, int Ci, int Co) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long idx = (long long)blockIdx.x * 8 + warp;
+    if (idx >= (long long)N * Co) return;
+    const int n = (int)(idx / Co), o = (int)(idx % Co);
+    float s = 0.f;
+    for (int i = lane; i < Ci; i += 32) {
+        const float v = __ldg(s_hat + (long long)n * Ci + i);
+        s = fmaf(v * v, __ldg(wsq + (long long)o * Ci + i), s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) dcoef[idx] = rsqrtf(s + 1e-8f);
+}
+
+}  // namespace shgan
+
+using namespace shgan;
+
+extern "C" int shgan_dense_fwd(const float* x0, int64_t x0_stride, int I0, const float* x1, int64_t x1_stride,
+                               const float* w, const float* bias, float* y, int64_t y_stride, int B, int I, int O,
+                               float wgain, float bgain, int act, float act_alpha, float act_gain, float act_clamp,
+                               void* stream) {
+    SHGAN_CHECK(x0 && w && y, "null pointer");
+    SHGAN_CHECK(B >= 0 && I >= 4 && O >= 1, "bad sizes");
+    SHGAN_CHECK(I % 4 == 0 && I0 % 4 == 0 && x0_stride % 4 == 0 && x1_stride % 4 == 0, "feature counts/strides must be multiples of 4");
+    SHGAN_CHECK(I0 >= 0 && I0 <= I && (I0 == I || x1), "second input missing");
+    if (B == 0) return 0;
+    dense_kernel<<<ceil_div(O, 8), 256, 0, (cudaStream_t)stream>>>(x0, x0_stride, I0, x1, x1_stride, w, bias, y, y_stride, B, I,
+                                                                   O, wgain, bgain, act, act_alpha, act_gain, act_clamp);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shgan_normalize_2nd_moment(const float* z, float* y, int B, int D, void* stream) {
+    SHGAN_CHECK(z && y && B >= 0 && D >= 1, "bad arguments");
+    if (B == 0) return 0;
+    normalize_2nd_moment_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(z, y, D);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shgan_style_prep(const float* styles, const float* wsq, float* s_hat, float* dcoef, int N, int Ci, int Co,
+                                int demod, float pre_scale, void* stream) {
+    SHGAN_CHECK(styles && s_hat, "null pointer");
+    SHGAN_CHECK(N >= 0 && Ci >= 1 && Co >= 1, "bad sizes");
+    SHGAN_CHECK(!demod || (wsq && dcoef), "demodulation needs wsq and dcoef");
+    if (N == 0) return 0;
+    style_scale_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(styles, s_hat, N * Ci, demod, pre_scale);
+    SHGAN_LAUNCH_CHECK();
+    if (demod) {
+        dcoef_kernel<<<(unsigned)ceil_div64((long long)N * Co, 8), 256, 0, (cudaStream_t)stream>>>(s_hat, wsq, dcoef, N, Ci, Co);
+        SHGAN_LAUNCH_CHECK();
+    }
+    return 0;
+}

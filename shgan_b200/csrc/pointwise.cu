@@ -1,0 +1,155 @@
+// Small-channel pointwise kernels at the two ends of the generator (sm_100a):
+//   * fromrgb : 1x1 conv Ci(<=8) -> Co with bias + lrelu_agc, reading the NCHW fp32 network input and
+//               writing the split-plane NHWC activation (lib/model_zoo/stylegan.py:226-238 for the
+//               encoder's fromrgb layer, comodgan.py:44-52).
+//   * torgb_combine : img = upsample2d(img_prev) + sum of the torgb partial sums produced by the conv
+//               epilogue + bias (comodgan.py:331-338, stylegan.py:325-337), optionally fused with the
+//               eval loop's composite + uint8 quantisation (lib/experiments/shgan_default.py:257-262).
+// Both are pure HBM streaming kernels; each thread owns one output pixel (x fastest) so the NCHW
+// reads/writes are coalesced, and fromrgb's NHWC plane stores are 16 B vectors.
+#include "common.cuh"
+
+namespace shgan {
+
+constexpr int FRGB_MAX_CI = 8;
+constexpr int FRGB_MAX_CO = 128;
+
+__global__ void __launch_bounds__(256)
+fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float wgain,
+               float act_alpha, float act_gain, float act_clamp, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+               int N, int Ci, int Co, int HW) {
+    __shared__ float s_w[FRGB_MAX_CO * FRGB_MAX_CI];
+    __shared__ float s_b[FRGB_MAX_CO];
+    for (int i = threadIdx.x; i < Co * Ci; i += blockDim.x) s_w[i] = w[i] * wgain;
+    for (int i = threadIdx.x; i < Co; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int cgs = Co / 8;
+    const long long total = (long long)N * HW * cgs;
+    for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(gid % cgs);
+        const long long pix = gid / cgs;           // n*HW + p
+        const int n = (int)(pix / HW);
+        const int p = (int)(pix - (long long)n * HW);
+        float xin[FRGB_MAX_CI];
+#pragma unroll
+        for (int i = 0; i < FRGB_MAX_CI; ++i) xin[i] = i < Ci ? __ldg(x + ((long long)n * Ci + i) * HW + p) : 0.f;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int o = cg * 8 + j;
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < FRGB_MAX_CI; ++i)
+                if (i < Ci) a = fmaf(xin[i], s_w[o * Ci + i], a);
+            v[j] = lrelu_agc(a + s_b[o], act_alpha, act_gain, act_clamp);
+        }
+        store_planes8(out_hi, out_lo, pix * Co + cg * 8, v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+torgb_combine_kernel(const float* __restrict__ img_prev, const float* __restrict__ rgb_partial, int n_blocks,
+                     const float* __restrict__ bias, const float* __restrict__ f, float* __restrict__ img_out, int N, int H,
+                     int W, const float* __restrict__ comp_x, uint8_t* __restrict__ comp_out) {
+    __shared__ float s_f[16];
+    if (threadIdx.x < 16) s_f[threadIdx.x] = f ? f[15 - threadIdx.x] * 4.f : 0.f;  // flipped filter * gain(up^2)
+    __syncthreads();
+    const long long total = (long long)N * H * W;
+    const int h2 = H / 2, w2 = W / 2;
+    for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(gid % W);
+        long long t = gid / W;
+        const int y = (int)(t % H);
+        const int n = (int)(t / H);
+        float v[3] = {0.f, 0.f, 0.f};
+        if (img_prev) {
+            // upfirdn2d(up=2, pad=[2,1,2,1]): tap (fy,fx) reads zero-inserted position (y+fy-2, x+fx-2), which holds
+            // img_prev[(y+fy-2)/2, (x+fx-2)/2] when both are even and in range (upfirdn2d.py:98-138, :279-314)
+            const int fy0 = y & 1, fx0 = x & 1;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int fy = fy0 + 2 * a;
+                const int Y = y + fy - 2;
+                if (Y < 0 || (Y >> 1) >= h2) continue;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int fx = fx0 + 2 * b;
+                    const int X = x + fx - 2;
+                    if (X < 0 || (X >> 1) >= w2) continue;
+                    const float fv = s_f[fy * 4 + fx];
+                    const long long ip = (long long)(Y >> 1) * w2 + (X >> 1);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        v[j] = fmaf(__ldg(img_prev + ((long long)n * 3 + j) * h2 * w2 + ip), fv, v[j]);
+                }
+            }
+        }
+        float r[3] = {0.f, 0.f, 0.f};
+        const float4* pp = reinterpret_cast<const float4*>(rgb_partial) + gid * n_blocks;
+        for (int b = 0; b < n_blocks; ++b) {
+            const float4 q = __ldg(pp + b);
+            r[0] += q.x; r[1] += q.y; r[2] += q.z;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            // reference order: img = upsample(img) + (conv + bias)
+            v[j] = __fadd_rn(v[j], __fadd_rn(r[j], bias ? __ldg(bias + j) : 0.f));
+            img_out[(((long long)n * 3 + j) * H + y) * W + x] = v[j];
+        }
+        if (comp_x) {
+            const long long hw = (long long)H * W, p = (long long)y * W + x;
+            const float m = __fadd_rn(__ldg(comp_x + (long long)n * 4 * hw + p), 0.5f);
+            const float om = __fsub_rn(1.f, m);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float xin = __ldg(comp_x + ((long long)n * 4 + 1 + j) * hw + p);
+                float o = __fadd_rn(__fmul_rn(xin, m), __fmul_rn(v[j], om));
+                o = __fadd_rn(__fmul_rn(o, 127.5f), 127.5f);
+                o = fminf(fmaxf(o, 0.f), 255.f);
+                comp_out[((long long)n * 3 + j) * hw + p] = (uint8_t)o;  // truncation, like .to(torch.uint8)
+            }
+        }
+    }
+}
+
+}  // namespace shgan
+
+using namespace shgan;
+
+extern "C" int shgan_fromrgb(const float* x, const float* w, const float* bias, float wgain, float act_alpha,
+                             float act_gain, float act_clamp, void* out_hi, void* out_lo, int N, int Ci, int Co, int H,
+                             int W, void* stream) {
+    SHGAN_CHECK(x && w && out_hi && out_lo, "null pointer");
+    SHGAN_CHECK(Ci >= 1 && Ci <= FRGB_MAX_CI, "Ci must be in 1..8");
+    SHGAN_CHECK(Co >= 8 && Co % 8 == 0 && Co <= FRGB_MAX_CO, "Co must be a multiple of 8, at most 128");
+    SHGAN_CHECK(N >= 0 && H >= 1 && W >= 1 && (long long)N * Co * H * W <= INT32_MAX, "bad tensor size");
+    if (N == 0) return 0;
+    const long long total = (long long)N * H * W * (Co / 8);
+    long long blocks = ceil_div64(total, 256);
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    fromrgb_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, w, bias, wgain, act_alpha, act_gain, act_clamp,
+                                                                       (__half*)out_hi, (__half*)out_lo, N, Ci, Co, H * W);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shgan_torgb_combine(const float* img_prev, const float* rgb_partial, int n_blocks, const float* bias,
+                                   const float* f, float* img_out, int N, int H, int W, const float* comp_x,
+                                   uint8_t* comp_out, void* stream) {
+    SHGAN_CHECK(rgb_partial && img_out, "null pointer");
+    SHGAN_CHECK(n_blocks >= 1, "n_blocks must be at least 1");
+    SHGAN_CHECK(!img_prev || f, "upsampling img_prev needs the 4x4 filter");
+    SHGAN_CHECK(!img_prev || (H % 2 == 0 && W % 2 == 0), "H and W must be even when img_prev is given");
+    SHGAN_CHECK((comp_x == nullptr) == (comp_out == nullptr), "comp_x/comp_out must both be set");
+    SHGAN_CHECK(N >= 0 && H >= 1 && W >= 1 && (long long)N * 4 * H * W * n_blocks <= INT32_MAX, "bad tensor size");
+    if (N == 0) return 0;
+    const long long total = (long long)N * H * W;
+    long long blocks = ceil_div64(total, 256);
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    torgb_combine_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(img_prev, rgb_partial, n_blocks, bias, f, img_out,
+                                                                             N, H, W, comp_x, comp_out);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,342 @@
+"""Fused generator-forward engine: the SH-GAN hot path as a fixed sequence of sm_100a kernel launches.
+
+`GeneratorEngine` reads the parameters of a `model_zoo.comodgan.Generator` (reference layout), packs them once
+into kernel operands (tap-major fp16 hi/lo weights, demodulation energy tables, SHU constants) and then runs
+    mapping -> encoder (+SHU) -> style affines / demod coefficients -> synthesis (+ fused torgb / skip adds)
+entirely through the C ABI.  Activations stay on the device in the split-plane NHWC layout between kernels;
+NCHW fp32 exists only at the network input and the RGB output (reference call: comodgan.py:449-481).
+
+Per-layer mapping of reference ops to launches:
+  encoder conv0 / b4.conv   : 1 x shgan_conv_igemm (bias + lrelu_agc fused)
+  encoder conv1 (down 2)    : shgan_fir_nhwc (blur -> 4 parity planes) + shgan_conv_igemm over the 4 planes
+  synthesis conv0 (up 2)    : 4 x shgan_conv_igemm RAW parity passes (transposed conv at algorithmic cost)
+                              + shgan_fir_nhwc (blur, demod, noise, bias, lrelu, +feats[res], next-layer style)
+  synthesis conv1 / b4.conv : 1 x shgan_conv_igemm (demod, noise, bias, lrelu, fused torgb, next-layer style)
+  torgb + img upsample      : shgan_torgb_combine
+"""
+import math
+
+import torch
+
+from . import kernels as K
+from . import packing as P
+from .kernels import Planes
+
+SQRT2 = math.sqrt(2.0)
+
+
+def _check_device(dev):
+    if dev.type != 'cuda':
+        raise RuntimeError('shgan_b200 runs on CUDA devices only (no CPU fallback): move the generator to cuda')
+
+
+class _Act:
+    def __init__(self, spec):
+        a = P.parse_activation(spec) if isinstance(spec, (str, type(None))) else spec
+        self.on = a is not None
+        self.alpha = a['alpha'] if a else 0.0
+        self.gain = a['gain'] if a else 1.0
+        self.clamp = (a['clamp'] if a and a['clamp'] is not None else -1.0)
+
+
+class GeneratorEngine:
+    """passes: 3 = fp32-class split-precision tensor-core convolutions (parity mode), 1 = single fp16 pass.
+    impl: 0 = tcgen05 kernel (product), 1 = fp32 FMA cross-check kernel (tests only)."""
+
+    def __init__(self, G, passes=3, impl=0):
+        self.G = G
+        self.passes = passes
+        self.impl = impl
+        self._sig = None
+        self._buf = {}
+
+    # ---- parameter packing ---------------------------------------------------------------------
+    def _signature(self):
+        sig = []
+        for t in list(self.G.parameters()) + list(self.G.buffers()):
+            sig.append((t.data_ptr(), t._version))
+        return tuple(sig)
+
+    def refresh(self):
+        """(Re)pack every kernel operand from the module's current parameters."""
+        G = self.G
+        enc, syn = G.encoder, G.synthesis
+        dev = next(G.parameters()).device
+        _check_device(dev)
+        self.dev = dev
+        self.res = syn.resolution
+        self.act = _Act(syn.activation)
+        f = syn.b4.conv.resample_filter if getattr(syn.b4.conv, 'resample_filter', None) is not None else None
+        f = P.setup_filter([1, 3, 3, 1]) if f is None else f
+        self.f = f.detach().to(dev, torch.float32).contiguous()               # as stored (upsample2d flips it itself)
+        self.f_applied = self.f.flip([0, 1]).contiguous()                     # correlation taps of upfirdn2d(flip_filter=False)
+
+        # mapping
+        m = G.mapping
+        self.map_layers = []
+        for i in range(m.num_layers):
+            fc = getattr(m, f'fc{i}')
+            self.map_layers.append((fc.weight.detach(), fc.bias.detach() if fc.bias is not None else None,
+                                    float(fc.weight_gain), float(fc.bias_gain), _Act(fc.activation_spec)))
+
+        # encoder
+        self.enc_res = list(enc.encode_res)
+        self.enc = {}
+        eact = _Act(enc.activation)
+        self.eact = eact
+        for idx, r in enumerate(self.enc_res[:-1]):
+            b = getattr(enc, f'b{r}')
+            d = {}
+            if b.fromrgb is not None:
+                w = b.fromrgb.weight.detach()
+                d['fromrgb'] = (w.reshape(w.shape[0], w.shape[1]).contiguous(), b.fromrgb.bias.detach(),
+                                float(b.fromrgb.weight_gain))
+            for nm in ('conv0', 'conv1'):
+                l = getattr(b, nm)
+                wh, wl = P.pack_conv_weight(l.weight)
+                d[nm] = dict(w_hi=wh, w_lo=wl, bias=l.bias.detach(), wgain=float(l.weight_gain),
+                             ci=l.weight.shape[1], co=l.weight.shape[0])
+            self.enc[r] = d
+        l = enc.b4.conv
+        wh, wl = P.pack_conv_weight(l.weight)
+        self.enc[4] = dict(conv=dict(w_hi=wh, w_lo=wl, bias=l.bias.detach(), wgain=float(l.weight_gain),
+                                     ci=l.weight.shape[1], co=l.weight.shape[0]),
+                           fc=(enc.b4.fc.weight.detach(), enc.b4.fc.bias.detach(), float(enc.b4.fc.weight_gain),
+                               float(enc.b4.fc.bias_gain), _Act(enc.b4.fc.activation_spec)))
+        # SHU
+        shu = getattr(enc, 'shu', None)
+        self.shu = None
+        if shu is not None:
+            c2 = shu.in_channels * 2
+            r_in, r_lo = shu.input_res, shu.lowest_res
+            masks = P.gaussian_band_masks(r_in, r_lo, shu.tail_sigma_mult, shu.gaussian_at_input_res)
+            self.shu = dict(
+                ch=shu.in_channels, input_res=r_in, lowest_res=r_lo, reslist=sorted(masks),
+                conv0_w=shu.conv0.weight.detach().reshape(c2, c2).contiguous(), conv0_b=shu.conv0.bias.detach(),
+                df1_w=shu.df1.weight.detach().contiguous(),
+                cw=P.make_cweight(shu.df1.freedom, (r_in, r_in // 2 + 1)).to(dev).contiguous(),
+                gauss=torch.cat([masks[r].reshape(-1) for r in sorted(masks)]).to(dev).contiguous())
+
+        # synthesis
+        self.syn_res = list(syn.block_res)
+        self.syn = {}
+        self.style_layers = []     # (name, ws index, affine w, affine b, demod, wsq, pre_scale, ci, co)
+
+        def syn_layer(l, name, widx):
+            w_hat, wsq = P.demod_weight(l.weight)
+            wh, wl = P.pack_conv_weight(w_hat)
+            self.style_layers.append(dict(name=name, widx=widx, aw=l.affine.weight.detach(), ab=l.affine.bias.detach(),
+                                          again=float(l.affine.weight_gain), demod=True, wsq=wsq, pre_scale=1.0,
+                                          ci=l.weight.shape[1], co=l.weight.shape[0]))
+            return dict(w_hi=wh, w_lo=wl, bias=l.bias.detach(), noise_const=l.noise_const.detach().contiguous(),
+                        noise_strength=l.noise_strength.detach(), ci=l.weight.shape[1], co=l.weight.shape[0],
+                        res=l.resolution, use_noise=l.use_noise)
+
+        def rgb_layer(l, name, widx):
+            w = l.weight.detach()
+            self.style_layers.append(dict(name=name, widx=widx, aw=l.affine.weight.detach(), ab=l.affine.bias.detach(),
+                                          again=float(l.affine.weight_gain), demod=False, wsq=None,
+                                          pre_scale=float(l.weight_gain), ci=w.shape[1], co=w.shape[0]))
+            wpad = torch.zeros((3, w.shape[1]), dtype=torch.float32, device=dev)
+            wpad[:w.shape[0]] = w.reshape(w.shape[0], w.shape[1])
+            bias = torch.zeros(3, dtype=torch.float32, device=dev)
+            bias[:w.shape[0]] = l.bias.detach()
+            return dict(w=wpad.contiguous(), bias=bias)
+
+        widx = 0
+        b4 = syn.b4
+        self.syn[4] = dict(fc=(b4.fc.weight.detach(), b4.fc.bias.detach(), float(b4.fc.weight_gain), float(b4.fc.bias_gain),
+                               _Act(b4.fc.activation_spec)),
+                           conv=syn_layer(b4.conv, 'b4.conv', widx), torgb=rgb_layer(b4.torgb, 'b4.torgb', widx + 1))
+        widx += 1
+        for r in self.syn_res[1:]:
+            b = getattr(syn, f'b{r}')
+            self.syn[r] = dict(conv0=syn_layer(b.conv0, f'b{r}.conv0', widx), conv1=syn_layer(b.conv1, f'b{r}.conv1', widx + 1),
+                               torgb=rgb_layer(b.torgb, f'b{r}.torgb', widx + 2))
+            widx += 2
+        self._sig = self._signature()
+
+    def _ensure(self):
+        if self._sig is None or self._sig != self._signature():
+            self.refresh()
+            self._buf = {}
+
+    # ---- buffers --------------------------------------------------------------------------------------
+    def _planes(self, name, n, h, w, c):
+        key = (name, n, h, w, c)
+        b = self._buf.get(key)
+        if b is None:
+            b = Planes.empty(n, h, w, c, self.dev)
+            self._buf[key] = b
+        return b
+
+    def _f32(self, name, *shape):
+        key = (name,) + tuple(shape)
+        b = self._buf.get(key)
+        if b is None:
+            b = torch.zeros(shape, dtype=torch.float32, device=self.dev)
+            self._buf[key] = b
+        return b
+
+    # ---- pieces -----------------------------------------------------------------------------------------
+    def _dense(self, spec, x0, out, x1=None):
+        w, b, wg, bg, act = spec
+        return K.dense(x0, w, b, out, wg, bg, act.on, act.alpha, act.gain, act.clamp, x1=x1)
+
+    def mapping(self, z):
+        """Mapping.forward (stylegan.py:394-430) for c_dim == 0, truncation_psi == 1 -> w [N, w_dim]."""
+        self._ensure()
+        n = z.shape[0]
+        x = K.normalize_2nd_moment(z.contiguous().float(), self._f32('map_in', n, z.shape[1]))
+        for i, spec in enumerate(self.map_layers):
+            x = self._dense(spec, x, self._f32(f'map{i}', n, spec[0].shape[0]))
+        return x
+
+    def _conv(self, srcs, L, taps, oh, ow, epi=None, raw=None):
+        K.conv_igemm(srcs, L['w_hi'], L['w_lo'], taps, oh, ow, epi=epi, raw=raw, passes=self.passes, impl=self.impl)
+
+    def _enc_epi(self, L, out):
+        a = self.eact
+        return K.make_epilogue(wgain=L['wgain'], bias=L['bias'], act=a.on, act_alpha=a.alpha, act_gain=a.gain,
+                               act_clamp=a.clamp, out=out)
+
+    def encoder(self, x):
+        """shgan.Encoder.forward (shgan.py:361-383) -> (x_global fp32 [N,oc_n], feats {res: Planes})."""
+        self._ensure()
+        x = x.contiguous().float()
+        n, _, R, _ = x.shape
+        feats = {}
+        a = None
+        ident = None
+        for r in self.enc_res[:-1]:
+            d = self.enc[r]
+            c = d['conv0']['ci']
+            if 'fromrgb' in d:
+                w, b, wg = d['fromrgb']
+                a = K.fromrgb(x, w, b, wg, self.eact.alpha, self.eact.gain, self.eact.clamp, self._planes(f'e{r}.rgb', n, r, r, c))
+            feat = self._planes(f'e{r}.feat', n, r, r, d['conv0']['co'])
+            self._conv([a], d['conv0'], P.taps_plain(3, 3), r, r, epi=self._enc_epi(d['conv0'], feat))
+            feats[r] = feat
+            # conv1: blur (pad 2) into four parity planes, then the stride-2 conv as a 4-source stride-1 conv
+            ph = (r + 1 + 1) // 2
+            c1 = d['conv1']['ci']
+            par = self._planes(f'e{r}.par', 4 * n, ph, ph, c1)
+            ident = K.make_epilogue(out=par)
+            K.fir_nhwc(feat, self.f_applied, 1.0, (2, 2, 2, 2), ident, parity_split=True)
+            srcs = [Planes(par.hi[q * n:(q + 1) * n], par.lo[q * n:(q + 1) * n]) for q in range(4)]
+            a = self._planes(f'e{r}.down', n, r // 2, r // 2, d['conv1']['co'])
+            self._conv(srcs, d['conv1'], P.taps_down2(3), r // 2, r // 2, epi=self._enc_epi(d['conv1'], a))
+        d = self.enc[4]
+        feat4 = self._planes('e4.feat', n, 4, 4, d['conv']['co'])
+        self._conv([a], d['conv'], P.taps_plain(3, 3), 4, 4, epi=self._enc_epi(d['conv'], feat4))
+        feats[4] = feat4
+        flat = K.planes_to_nchw(feat4, out=self._f32('e4.flat', n, d['conv']['co'], 4, 4))
+        x_global = self._dense(d['fc'], flat.view(n, -1), self._f32('x_global', n, d['fc'][0].shape[0]))
+        if self.shu is not None:
+            s = self.shu
+            ch, rin = s['ch'], s['input_res']
+            fin = feats[rin]
+            xin = K.planes_to_nchw(fin, c_off=fin.shape[3] - ch, c=ch, out=self._f32('shu.in', n, ch, rin, rin))
+            outs = [self._f32(f'shu.out{r}', n, ch, r, r) for r in s['reslist']]
+            ws = self._buf.get(('shu.ws', n))
+            if ws is None:
+                ws = torch.empty(K.shu_workspace_bytes(n, ch, rin), dtype=torch.uint8, device=self.dev)
+                self._buf[('shu.ws', n)] = ws
+            K.shu_fwd(xin, s['conv0_w'], s['conv0_b'], s['df1_w'], s['cw'], s['gauss'], outs, s['lowest_res'], workspace=ws)
+            for r, o in zip(s['reslist'], outs):
+                K.planes_add_nchw(feats[r], o, feats[r].shape[3] - ch)   # feats[r][:, -ch:] += shu[r]  (shgan.py:378-382)
+        return x_global, feats
+
+    def styles(self, ws, x_global):
+        """Affine transforms + style normalisation / demodulation coefficients for every synthesis layer
+        (stylegan.py:280, 331 and :145-155).  ws [N,num_ws,w_dim] (any strides with unit inner stride)."""
+        n = x_global.shape[0]
+        out = {}
+        for L in self.style_layers:
+            raw = self._f32('st.raw.' + L['name'], n, L['ci'])
+            K.dense(ws[:, L['widx']], L['aw'], L['ab'], raw, L['again'], 1.0, False, x1=x_global)
+            s_hat = self._f32('st.hat.' + L['name'], n, L['ci'])
+            dcoef = self._f32('st.dc.' + L['name'], n, L['co']) if L['demod'] else None
+            K.style_prep(raw, L['wsq'], s_hat, dcoef, L['demod'], L['pre_scale'])
+            out[L['name']] = (s_hat, dcoef)
+        return out
+
+    def _noise(self, L, n, noise_mode, gen=None):
+        if not L['use_noise'] or noise_mode == 'none':
+            return None, 0
+        r = L['res']
+        if noise_mode == 'const':
+            return L['noise_const'], 0
+        return torch.randn([n, 1, r, r], device=self.dev, generator=gen), r * r  # stylegan.py:282-283
+
+    def synthesis(self, x_global, feats, ws, noise_mode='random', comp_x=None):
+        """comodgan.Synthesis.forward (comodgan.py:396-433).  Returns img fp32 [N,3,R,R] (+ uint8 composite)."""
+        self._ensure()
+        n = x_global.shape[0]
+        act = self.act
+        st = self.styles(ws, x_global)
+        names = [L['name'] for L in self.style_layers]
+
+        def next_conv_style(name):
+            i = names.index(name) + 1
+            while i < len(names) and names[i].endswith('torgb'):
+                i += 1
+            return st[names[i]][0] if i < len(names) else None
+
+        d = self.syn[4]
+        c4 = d['conv']['ci']
+        x0 = self._dense(d['fc'], x_global, self._f32('s4.fc', n, d['fc'][0].shape[0]))
+        x = K.nchw_to_planes(x0.view(n, c4, 4, 4), add=feats[4], scale=st['b4.conv'][0], out=self._planes('s4.in', n, 4, 4, c4))
+        img = None
+        last = self.syn_res[-1]
+        comp = None
+        for r in self.syn_res:
+            d = self.syn[r]
+            if r == 4:
+                L, name = d['conv'], 'b4.conv'
+            else:
+                # conv0: stride-2 transposed conv as four parity passes at algorithmic cost, then blur + epilogue
+                L0, name0 = d['conv0'], f'b{r}.conv0'
+                h = r // 2
+                z = self._f32(f's{r}.z', n, 2 * h + 1, 2 * h + 1, L0['co'])
+                for py in range(2):
+                    for px in range(2):
+                        self._conv([x], L0, P.taps_up2(py, px), P.up2_pass_size(h, py), P.up2_pass_size(h, px),
+                                   raw=(z, 2, 2, py, px))
+                nz, sn = self._noise(L0, n, noise_mode)
+                y = self._planes(f's{r}.mid', n, r, r, L0['co'])
+                epi = K.make_epilogue(dcoef=st[name0][1], noise=nz, noise_sn=sn, noise_strength=L0['noise_strength'],
+                                      bias=L0['bias'], act=act.on, act_alpha=act.alpha, act_gain=act.gain, act_clamp=act.clamp,
+                                      skip=feats[r], next_scale=st[f'b{r}.conv1'][0], out=y)
+                K.fir_nhwc(z, self.f_applied, 4.0, (1, 1, 1, 1), epi)
+                x = y
+                L, name = d['conv1'], f'b{r}.conv1'
+            nz, sn = self._noise(L, n, noise_mode)
+            nblk = K.conv_num_nblocks(L['co'])
+            part = self._f32(f's{r}.rgb', n, r, r, nblk, 4)
+            nxt = next_conv_style(name)
+            out = self._planes(f's{r}.out', n, r, r, L['co']) if r != last else None
+            epi = K.make_epilogue(dcoef=st[name][1], noise=nz, noise_sn=sn, noise_strength=L['noise_strength'], bias=L['bias'],
+                                  act=act.on, act_alpha=act.alpha, act_gain=act.gain, act_clamp=act.clamp,
+                                  rgb_w=d['torgb']['w'], rgb_style=st[f'b{r}.torgb'][0], rgb_out=part,
+                                  next_scale=nxt if out is not None else None, out=out)
+            self._conv([x], L, P.taps_plain(3, 3), r, r, epi=epi)
+            img_r = self._f32(f's{r}.img', n, 3, r, r)
+            if r == last and comp_x is not None:
+                comp = torch.empty((n, 3, r, r), dtype=torch.uint8, device=self.dev)
+            K.torgb_combine(img, part, d['torgb']['bias'], self.f, img_r, comp_x=comp_x if r == last else None,
+                            comp_out=comp if r == last else None)
+            img = img_r
+            x = out
+        return (img, comp) if comp_x is not None else img
+
+    def forward(self, x, z, noise_mode='random', composite=False):
+        """comodgan.Generator.forward (comodgan.py:449-481).  composite=True additionally returns the eval loop's
+        uint8 composite (shgan_default.py:257-262) fused into the last kernel."""
+        self._ensure()
+        w = self.mapping(z)
+        num_ws = self.G.num_ws
+        ws = w.unsqueeze(1).expand(w.shape[0], num_ws, w.shape[1])
+        x = x.contiguous().float()
+        x_global, feats = self.encoder(x)
+        return self.synthesis(x_global, feats, ws, noise_mode=noise_mode, comp_x=x if composite else None)

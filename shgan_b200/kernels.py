@@ -1,0 +1,243 @@
+"""Thin torch-tensor wrappers over the C ABI (include/shgan_b200.h).
+
+PyTorch is used only for device memory and streams: every function takes CUDA tensors, passes their raw
+device pointers plus the current torch stream to the library, and returns the caller-visible outputs.
+Nothing here computes on the CPU and there is no fallback implementation.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, Epilogue
+
+SQRT2 = math.sqrt(2.0)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError(f'{name} must be a contiguous float32 CUDA tensor')
+    return t
+
+
+class Planes:
+    """Split-plane NHWC activation: value = hi + lo, both fp16 [N,H,W,C] (include/shgan_b200.h)."""
+    __slots__ = ('hi', 'lo')
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(n, h, w, c, device):
+        # zero-filled once: rows/columns that kernels never write (parity padding) must not hold NaN patterns
+        return Planes(torch.zeros((n, h, w, c), dtype=torch.float16, device=device),
+                      torch.zeros((n, h, w, c), dtype=torch.float16, device=device))
+
+    @property
+    def shape(self):
+        return tuple(self.hi.shape)
+
+    def float(self):
+        """fp32 NHWC view of the value (test helper; not used on the hot path)."""
+        return self.hi.float() + self.lo.float()
+
+
+def make_epilogue(dcoef=None, wgain=1.0, noise=None, noise_sn=0, noise_strength=None, bias=None, act=False,
+                  act_alpha=0.2, act_gain=1.0, act_clamp=-1.0, skip=None, next_scale=None, rgb_w=None,
+                  rgb_style=None, rgb_out=None, out=None, out_f32=None):
+    e = Epilogue()
+    e.dcoef = _p(dcoef); e.wgain = wgain
+    e.noise = _p(noise); e.noise_sn = noise_sn; e.noise_strength = _p(noise_strength)
+    e.bias = _p(bias); e.act = 1 if act else 0
+    e.act_alpha = act_alpha; e.act_gain = act_gain; e.act_clamp = act_clamp
+    e.skip_hi = _p(skip.hi) if skip is not None else None
+    e.skip_lo = _p(skip.lo) if skip is not None else None
+    e.next_scale = _p(next_scale); e.rgb_w = _p(rgb_w); e.rgb_style = _p(rgb_style); e.rgb_out = _p(rgb_out)
+    e.out_hi = _p(out.hi) if out is not None else None
+    e.out_lo = _p(out.lo) if out is not None else None
+    e.out_f32 = _p(out_f32)
+    return e
+
+
+# ---- upfirdn2d -----------------------------------------------------------------------------------
+def upfirdn2d_fwd(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+    """Same contract as the reference pybind op (upfirdn2d.cpp:16): allocates and returns y."""
+    _f32c(x, 'x'); _f32c(f, 'f')
+    n, c, h, w = x.shape
+    fh, fw = f.shape
+    ow = (w * upx + padx0 + padx1 - fw + downx) // downx
+    oh = (h * upy + pady0 + pady1 - fh + downy) // downy
+    if ow < 1 or oh < 1:
+        raise RuntimeError('upfirdn2d: output must be at least 1x1')
+    y = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.shgan_upfirdn2d_fwd(_p(x), _p(f), _p(y), n, c, h, w, fh, fw, upx, upy, downx, downy,
+                                      padx0, padx1, pady0, pady1, 1 if flip else 0, float(gain), _stream()),
+               'shgan_upfirdn2d_fwd')
+    return y
+
+
+# ---- layout ----------------------------------------------------------------------------------------
+def nchw_to_planes(x, add=None, scale=None, out=None, c_off=0):
+    _f32c(x, 'x')
+    n, c, h, w = x.shape
+    if out is None:
+        out = Planes.empty(n, h, w, c, x.device)
+    c_tot = out.shape[3]
+    lib = _lib.load()
+    _lib.check(lib.shgan_nchw_to_planes(_p(x), _p(add.hi) if add is not None else None,
+                                       _p(add.lo) if add is not None else None, _p(scale), _p(out.hi), _p(out.lo),
+                                       n, c, h, w, c_off, c_tot, _stream()), 'shgan_nchw_to_planes')
+    return out
+
+
+def planes_to_nchw(p, c_off=0, c=None, out=None):
+    n, h, w, c_tot = p.shape
+    c = c_tot - c_off if c is None else c
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=p.hi.device)
+    lib = _lib.load()
+    _lib.check(lib.shgan_planes_to_nchw(_p(p.hi), _p(p.lo), _p(out), n, c, h, w, c_off, c_tot, _stream()),
+               'shgan_planes_to_nchw')
+    return out
+
+
+def planes_add_nchw(p, x, c_off):
+    _f32c(x, 'x')
+    n, c, h, w = x.shape
+    lib = _lib.load()
+    _lib.check(lib.shgan_planes_add_nchw(_p(p.hi), _p(p.lo), _p(x), n, c, h, w, c_off, p.shape[3], _stream()),
+               'shgan_planes_add_nchw')
+    return p
+
+
+def nhwc_to_nchw_f32(x):
+    _f32c(x, 'x')
+    n, h, w, c = x.shape
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.shgan_nhwc_to_nchw_f32(_p(x), _p(y), n, c, h, w, _stream()), 'shgan_nhwc_to_nchw_f32')
+    return y
+
+
+# ---- convolution -------------------------------------------------------------------------------------
+def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0):
+    """srcs: list of Planes [N,Hs,Ws,C]; w_hi/w_lo: fp16 [w_taps, Co, C]; taps: list of (src, dy, dx, w_tap).
+    epi: Epilogue (ACT mode)  or  raw = (z fp32 [N,ZH,ZW,Co], zsy, zsx, zoy, zox) (RAW mode)."""
+    d = ConvDesc()
+    d.num_src = len(srcs)
+    n, _, _, c = srcs[0].shape
+    for i, s in enumerate(srcs):
+        d.src_hi[i] = _p(s.hi); d.src_lo[i] = _p(s.lo)
+        d.src_h[i] = s.shape[1]; d.src_w[i] = s.shape[2]
+    d.N = n; d.C = c; d.Co = w_hi.shape[1]
+    d.w_hi = _p(w_hi); d.w_lo = _p(w_lo); d.w_taps = w_hi.shape[0]
+    d.ntaps = len(taps)
+    for i, (s, dy, dx, wt) in enumerate(taps):
+        d.tap_src[i] = s; d.tap_dy[i] = dy; d.tap_dx[i] = dx; d.tap_w[i] = wt
+    d.OH = oh; d.OW = ow
+    if raw is not None:
+        z, zsy, zsx, zoy, zox = raw
+        d.mode = 1; d.z = _p(z); d.ZH = z.shape[1]; d.ZW = z.shape[2]
+        d.zsy = zsy; d.zsx = zsx; d.zoy = zoy; d.zox = zox
+    else:
+        d.mode = 0
+        d.epi = epi
+    d.block_n = block_n; d.passes = passes; d.impl = impl
+    lib = _lib.load()
+    _lib.check(lib.shgan_conv_igemm(C.byref(d), _stream()), 'shgan_conv_igemm')
+
+
+def conv_num_nblocks(co, block_n=0):
+    return _lib.load().shgan_conv_num_nblocks(co, block_n)
+
+
+def fir_nhwc(src, f, gain, pads, epi, parity_split=False):
+    """src: Planes or fp32 NHWC tensor; pads = (pad_x0, pad_x1, pad_y0, pad_y1); f: fp32 [4,4] (as applied)."""
+    lib = _lib.load()
+    if isinstance(src, Planes):
+        n, ih, iw, c = src.shape
+        args = (None, _p(src.hi), _p(src.lo))
+    else:
+        _f32c(src, 'src')
+        n, ih, iw, c = src.shape
+        args = (_p(src), None, None)
+    _lib.check(lib.shgan_fir_nhwc(*args, _p(f), f.shape[0], f.shape[1], float(gain), n, c, ih, iw,
+                                 pads[0], pads[1], pads[2], pads[3], C.byref(epi), 1 if parity_split else 0, _stream()),
+               'shgan_fir_nhwc')
+
+
+# ---- pointwise ---------------------------------------------------------------------------------------
+def fromrgb(x, w, bias, wgain, act_alpha, act_gain, act_clamp, out):
+    _f32c(x, 'x')
+    n, ci, h, wd = x.shape
+    lib = _lib.load()
+    _lib.check(lib.shgan_fromrgb(_p(x), _p(w), _p(bias), wgain, act_alpha, act_gain, act_clamp, _p(out.hi), _p(out.lo),
+                                n, ci, out.shape[3], h, wd, _stream()), 'shgan_fromrgb')
+    return out
+
+
+def torgb_combine(img_prev, rgb_partial, bias, f, img_out, comp_x=None, comp_out=None):
+    n, _, h, w = img_out.shape
+    lib = _lib.load()
+    _lib.check(lib.shgan_torgb_combine(_p(img_prev), _p(rgb_partial), rgb_partial.shape[3], _p(bias), _p(f), _p(img_out),
+                                      n, h, w, _p(comp_x), _p(comp_out), _stream()), 'shgan_torgb_combine')
+    return img_out
+
+
+# ---- dense / styles ------------------------------------------------------------------------------------
+def dense(x0, w, bias, out, wgain, bgain=1.0, act=False, act_alpha=0.2, act_gain=SQRT2, act_clamp=256.0, x1=None):
+    """out[b,o] = act((cat[x0,x1][b] . w[o]) * wgain + bias[o]*bgain).  x0/x1/out may be strided row views."""
+    b, i0 = x0.shape
+    i = i0 + (x1.shape[1] if x1 is not None else 0)
+    o = w.shape[0]
+    assert w.shape[1] == i and x0.stride(1) == 1 and out.stride(1) == 1
+    lib = _lib.load()
+    _lib.check(lib.shgan_dense_fwd(_p(x0), x0.stride(0), i0, _p(x1), x1.stride(0) if x1 is not None else 0, _p(w), _p(bias),
+                                  _p(out), out.stride(0), b, i, o, wgain, bgain, 1 if act else 0, act_alpha, act_gain,
+                                  act_clamp, _stream()), 'shgan_dense_fwd')
+    return out
+
+
+def normalize_2nd_moment(z, out=None):
+    _f32c(z, 'z')
+    out = torch.empty_like(z) if out is None else out
+    lib = _lib.load()
+    _lib.check(lib.shgan_normalize_2nd_moment(_p(z), _p(out), z.shape[0], z.shape[1], _stream()),
+               'shgan_normalize_2nd_moment')
+    return out
+
+
+def style_prep(styles, wsq, s_hat, dcoef, demod, pre_scale=1.0):
+    n, ci = styles.shape
+    co = dcoef.shape[1] if dcoef is not None else 1
+    lib = _lib.load()
+    _lib.check(lib.shgan_style_prep(_p(styles), _p(wsq), _p(s_hat), _p(dcoef), n, ci, co, 1 if demod else 0, pre_scale,
+                                   _stream()), 'shgan_style_prep')
+
+
+# ---- SHU -----------------------------------------------------------------------------------------------
+def shu_workspace_bytes(n, c, r):
+    return int(_lib.load().shgan_shu_workspace_bytes(n, c, r))
+
+
+def shu_fwd(x, conv0_w, conv0_b, df1_w, cw, gauss, outs, lowest_res, workspace=None):
+    """x fp32 [N,C,R,R]; outs: list of fp32 [N,C,r,r] for r = lowest_res*2^k; gauss: concatenated band masks."""
+    _f32c(x, 'x')
+    n, c, r, _ = x.shape
+    if workspace is None:
+        workspace = torch.empty(shu_workspace_bytes(n, c, r), dtype=torch.uint8, device=x.device)
+    arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+    lib = _lib.load()
+    _lib.check(lib.shgan_shu_fwd(_p(x), _p(conv0_w), _p(conv0_b), _p(df1_w), _p(cw), _p(gauss), _p(workspace), arr,
+                                len(outs), n, c, r, lowest_res, _stream()), 'shgan_shu_fwd')
+    return outs

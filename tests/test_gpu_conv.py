@@ -1,0 +1,193 @@
+"""GPU parity tests of the convolution hot path (`-m gpu`).  Test names carry `simt` (fp32 FMA cross-check
+kernel, desc.impl=1) or `tc` (tcgen05 tensor-core kernel, the product path) so the two can be run in separate
+processes: `pytest -m gpu -k "not tc"` then `pytest -m gpu -k tc`.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle import shgan_oracle as O  # noqa: E402  (checker only)
+from golden.make_golden import CONV_CASES, MODCONV_CASES, modconv_inputs, rng, GENERATOR_CASES  # noqa: E402
+import helpers as H  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+IMPLS = [pytest.param(1, id='simt'), pytest.param(0, id='tc')]
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+# ------------------------------------------------------------------------------- raw igemm vs oracle conv
+def _igemm_plain(x, w, impl, passes=3, block_n=0):
+    """x NCHW, w [Co,Ci,3,3] -> NCHW via the planes kernels (3x3, stride 1, pad 1)."""
+    from shgan_b200 import kernels as K, packing as P
+    xp = K.nchw_to_planes(t(x))
+    wh, wl = P.pack_conv_weight(t(w))
+    n, _, h, wd = x.shape
+    y = torch.empty((n, h, wd, w.shape[0]), device=DEV)
+    K.conv_igemm([xp], wh, wl, P.taps_plain(3, 3), h, wd, epi=K.make_epilogue(out_f32=y), passes=passes, impl=impl, block_n=block_n)
+    return K.nhwc_to_nchw_f32(y).cpu().numpy()
+
+
+SHAPES = [
+    # n, ci, co, h, w
+    (3, 64, 64, 16, 16),     # one tile per image pair
+    (2, 128, 64, 24, 40),    # 2 K slabs, ragged tiles in x and y
+    (5, 64, 128, 4, 4),      # TN = 8 images per tile, ragged batch, BN = 128
+    (3, 64, 256, 8, 8),      # TN = 2, BN = 256
+    (1, 192, 64, 5, 7),      # odd sizes -> pow2 tile larger than the image
+    (2, 64, 512, 9, 33),     # 2 N blocks of 256
+]
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('shape', SHAPES, ids=[str(s) for s in SHAPES])
+def test_igemm_plain(shape, impl):
+    n, ci, co, h, w = shape
+    g = np.random.default_rng(abs(hash(shape)) % 1000)
+    x = g.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = g.standard_normal((co, ci, 3, 3)).astype(np.float32)
+    y = _igemm_plain(x, wt, impl)
+    ref = O.conv2d(x.astype(np.float64), wt.astype(np.float64), padding=1)
+    assert relerr(y, ref) <= 3e-6, relerr(y, ref)
+
+
+def test_igemm_tc_single_pass_and_block_n():
+    g = np.random.default_rng(11)
+    x = g.standard_normal((2, 64, 16, 16)).astype(np.float32)
+    wt = g.standard_normal((256, 64, 3, 3)).astype(np.float32)
+    ref = O.conv2d(x.astype(np.float64), wt.astype(np.float64), padding=1)
+    y1 = _igemm_plain(x, wt, 0, passes=1)
+    assert 1e-5 < relerr(y1, ref) <= 3e-3      # fp16-rounded operands: visibly worse than the split path, still sane
+    for bn in (64, 128, 256):
+        assert relerr(_igemm_plain(x, wt, 0, block_n=bn), ref) <= 3e-6
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv2d_resample_golden(case, impl, golden):
+    from shgan_b200 import ops
+    name, c = case
+    i = [k[0] for k in CONV_CASES].index(name)
+    g = rng(200 + i)
+    x = g.standard_normal((2, c['ci'], c['hw'], c['hw'])).astype(np.float32)
+    w = g.standard_normal((c['co'], c['ci'], c['k'], c['k'])).astype(np.float32)
+    f = O.setup_filter([1, 3, 3, 1]) if (c['up'] > 1 or c['down'] > 1) else None
+    y = ops.conv2d_resample(t(x), t(w), f=None if f is None else t(f), up=c['up'], down=c['down'], padding=c['k'] // 2,
+                            flip_weight=c['flip_weight'], impl=impl).cpu().numpy()
+    ref = golden('conv2d_resample')[name]
+    assert y.shape == ref.shape
+    assert relerr(y, ref) <= 5e-6, relerr(y, ref)
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('case', MODCONV_CASES, ids=[c[0] for c in MODCONV_CASES])
+def test_modulated_conv2d_golden(case, impl, golden):
+    from shgan_b200 import ops
+    name, c = case
+    i = [k[0] for k in MODCONV_CASES].index(name)
+    x, w, s, nz = modconv_inputs(i, c)
+    f = O.setup_filter([1, 3, 3, 1]) if c['up'] > 1 else None
+    y = ops.modulated_conv2d(t(x), t(w), t(s), noise=None if nz is None else t(nz), up=c['up'], padding=c['k'] // 2,
+                             resample_filter=None if f is None else t(f), demodulate=c['demod'], flip_weight=(c['up'] == 1),
+                             impl=impl).cpu().numpy()
+    ref = golden('modulated_conv2d')[name]
+    assert y.shape == ref.shape
+    assert relerr(y, ref) <= 1e-5, relerr(y, ref)
+
+
+# ------------------------------------------------------------------------------- whole generator vs golden
+def _run_generator(name, impl, golden, passes=3):
+    _, res, chb, chm, batch, seed = [c for c in GENERATOR_CASES if c[0] == name][0]
+    sd = O.synthetic_state_dict(res, seed=seed, ch_base=chb, ch_max=chm)
+    G = H.build_generator(res, sd, chb, chm, device=DEV)
+    G.engine(passes=passes, impl=impl)
+    x, z = O.synthetic_inputs(batch, res, seed=seed)
+    g = golden(name)
+    img, comp = G.forward_composite(t(x), t(z), noise_mode='const')
+    img2 = G(t(x), t(z), torch.zeros(batch, 0, device=DEV), noise_mode='const')
+    assert torch.equal(img, img2)                                    # deterministic
+    xg, feats = G.encoder(t(x))
+    return g, img.cpu().numpy(), comp.cpu().numpy(), xg.cpu().numpy(), {r: v.cpu().numpy() for r, v in feats.items()}
+
+
+def _check_generator(name, impl, golden, tol):
+    g, img, comp, xg, feats = _run_generator(name, impl, golden)
+    err = np.abs(img.astype(np.float64) - g['img']).max()
+    print(f'{name} impl={impl}: |img|max {np.abs(g["img"]).max():.3f} max-abs err {err:.3e}')
+    assert relerr(xg, g['x_global']) <= 2e-5
+    for r in (4, 8, 16):
+        assert relerr(feats[r], g[f'feat{r}']) <= 2e-5, r
+    for r, v in feats.items():
+        st = g[f'feat{r}_stats']
+        assert abs(v.std() - st[1]) <= 1e-4 * st[1] and abs(np.abs(v).max() - st[2]) <= 1e-4 * st[2], r
+    assert err <= tol, err
+    d = np.abs(comp.astype(int) - g['composite_u8'].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 2e-3
+
+
+def test_generator_simt_gen128(golden):
+    _check_generator('gen128_c64', 1, golden, 1e-3)
+
+
+def test_generator_tc_gen128(golden):
+    _check_generator('gen128_c64', 0, golden, 1e-3)
+
+
+def test_generator_tc_gen256(golden):
+    _check_generator('gen256', 0, golden, 1e-3)        # north_star: within 1e-3 max-abs of the reference
+
+
+def test_generator_tc_gen512(golden):
+    _check_generator('gen512', 0, golden, 1e-3)
+
+
+def test_generator_tc_vs_simt_batch_and_random_noise():
+    """Full-size 256^2 model, batch 3: the tensor-core path must agree with the fp32 FMA kernel on identical
+    operands, including noise_mode='random' under a fixed seed and batch-size independence of each sample."""
+    sd = O.synthetic_state_dict(256, seed=3)
+    G = H.build_generator(256, sd, device=DEV)
+    x, z = O.synthetic_inputs(3, 256, seed=3)
+    outs = {}
+    for impl in (1, 0):
+        G.engine(impl=impl)
+        torch.manual_seed(123)
+        outs[impl] = G(t(x), t(z), None, noise_mode='random').cpu().numpy()
+    scale = np.abs(outs[1]).max()
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-5 * max(1.0, scale)
+    G.engine(impl=0)
+    torch.manual_seed(123)
+    again = G(t(x), t(z), None, noise_mode='random').cpu().numpy()
+    assert np.array_equal(again, outs[0])
+    one = G(t(x[:1]), t(z[:1]), None, noise_mode='const').cpu().numpy()
+    three = G(t(x), t(z), None, noise_mode='const').cpu().numpy()
+    # the batch-global style normaliser (stylegan.py:147) cancels in the demodulation up to its 1e-8 epsilon
+    assert np.abs(one[0] - three[0]).max() <= 1e-3 * max(1.0, np.abs(three).max())
+
+
+def test_generator_tc_state_dict_reload_and_deepcopy():
+    import copy
+    sd1 = O.synthetic_state_dict(128, seed=1, ch_base=8192, ch_max=64)
+    sd2 = O.synthetic_state_dict(128, seed=2, ch_base=8192, ch_max=64)
+    G = H.build_generator(128, sd1, 8192, 64, device=DEV)
+    x, z = O.synthetic_inputs(2, 128, seed=1)
+    a = G(t(x), t(z), None, noise_mode='const').cpu().numpy()
+    G2 = copy.deepcopy(G)
+    G.load_state_dict({k: torch.from_numpy(v) for k, v in sd2.items()}, strict=True)   # must invalidate the packed operands
+    b = G(t(x), t(z), None, noise_mode='const').cpu().numpy()
+    assert np.abs(a - b).max() > 1e-2
+    assert np.array_equal(G2(t(x), t(z), None, noise_mode='const').cpu().numpy(), a)
+    ref = O.generator(sd2, x, z, 128)
+    assert np.abs(b - ref).max() <= 1e-3

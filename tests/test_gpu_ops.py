@@ -1,0 +1,227 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): every kernel is called through the C ABI (ctypes) and
+compared with the CPU oracle / the golden fixtures generated from the reference (tests/golden/make_golden.py).
+
+Tolerances: the reference path is fp32; all kernels here accumulate in fp32 (convolutions: fp16 hi/lo split
+operands, fp32 TMEM accumulation, dropped term < 2^-22), so op-level results must agree with the reference to
+fp32 rounding: 2e-5 relative to the output scale unless stated otherwise.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle import shgan_oracle as O  # noqa: E402  (checker only)
+from golden.make_golden import UPFIRDN_CASES, CONV_CASES, MODCONV_CASES, get_filter, modconv_inputs, rng  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+# ---------------------------------------------------------------------------------------------- upfirdn2d
+@pytest.mark.parametrize('case', UPFIRDN_CASES, ids=[c[0] for c in UPFIRDN_CASES])
+def test_upfirdn2d_golden(case, golden):
+    from shgan_b200 import ops
+    name, shape, fk, kw = case
+    i = [c[0] for c in UPFIRDN_CASES].index(name)
+    x = rng(100 + i).standard_normal(shape).astype(np.float32)
+    f = get_filter(fk)
+    y = ops.upfirdn2d(t(x), None if f is None else t(f), **kw).cpu().numpy()
+    ref = golden('upfirdn2d')[name]
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+
+
+def test_upfirdn2d_wrappers_and_sizes():
+    from shgan_b200 import ops
+    f = O.setup_filter([1, 3, 3, 1])
+    g = np.random.default_rng(0)
+    for shape in [(2, 5, 33, 47), (1, 3, 64, 64), (3, 2, 129, 130)]:
+        x = g.standard_normal(shape).astype(np.float32)
+        for fn, ofn, kw in [(ops.upsample2d, O.upsample2d, {}), (ops.downsample2d, O.downsample2d, {}),
+                            (ops.filter2d, O.filter2d, dict(gain=2.0)),
+                            (ops.upfirdn2d, O.upfirdn2d, dict(padding=[2, 2, 2, 2])),
+                            (ops.upfirdn2d, O.upfirdn2d, dict(padding=[1, 1, 1, 1], gain=4))]:
+            y = fn(t(x), t(f), **kw).cpu().numpy()
+            ref = ofn(x, f, **kw)
+            assert y.shape == ref.shape
+            assert np.abs(y - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), (fn.__name__, shape)
+
+
+def test_upfirdn2d_errors():
+    from shgan_b200 import ops
+    f = t(O.setup_filter([1, 3, 3, 1]))
+    with pytest.raises(RuntimeError):
+        ops.upfirdn2d(torch.zeros(1, 1, 4, 4), f.cpu())            # no CPU path
+    with pytest.raises(RuntimeError):
+        ops.upfirdn2d(torch.zeros(1, 1, 2, 2, device=DEV), f, padding=[-3, -3, -3, -3])   # output < 1x1
+    y = ops.upfirdn2d(torch.zeros(0, 3, 8, 8, device=DEV), f, padding=1)  # empty batch
+    assert y.shape == (0, 3, 7, 7)
+
+
+# ---------------------------------------------------------------------------------------------- layout
+def test_layout_roundtrip():
+    from shgan_b200 import kernels as K
+    g = np.random.default_rng(1)
+    x = (g.standard_normal((3, 40, 9, 13)) * 10).astype(np.float32)
+    p = K.nchw_to_planes(t(x))
+    back = K.planes_to_nchw(p).cpu().numpy()
+    assert np.abs(back - x).max() <= 1e-6 * np.abs(x).max()
+    # slice add: planes[:, :, :, 8:24] += y
+    y = g.standard_normal((3, 16, 9, 13)).astype(np.float32)
+    K.planes_add_nchw(p, t(y), 8)
+    ref = x.copy()
+    ref[:, 8:24] += y
+    back = K.planes_to_nchw(p).cpu().numpy()
+    assert np.abs(back - ref).max() <= 2e-6 * np.abs(ref).max()
+    sl = K.planes_to_nchw(p, c_off=8, c=16).cpu().numpy()
+    assert np.abs(sl - ref[:, 8:24]).max() <= 2e-6 * np.abs(ref).max()
+    # add + scale
+    sc = g.standard_normal((3, 40)).astype(np.float32)
+    q = K.nchw_to_planes(t(x), add=p, scale=t(sc))
+    ref2 = (x + ref) * sc[:, :, None, None]
+    assert np.abs(K.planes_to_nchw(q).cpu().numpy() - ref2).max() <= 3e-6 * np.abs(ref2).max()
+    z = g.standard_normal((2, 7, 5, 24)).astype(np.float32)
+    assert np.array_equal(K.nhwc_to_nchw_f32(t(z)).cpu().numpy(), z.transpose(0, 3, 1, 2))
+
+
+# ---------------------------------------------------------------------------------------------- small ops
+def test_dense_mapping_golden(golden):
+    from shgan_b200 import kernels as K
+    g = golden('small_ops')
+    out = torch.empty((5, 24), device=DEV)
+    K.dense(t(g['dense_x']), t(g['dense_w']), t(g['dense_b']), out, 0.5 / np.sqrt(40), 0.5, True, 0.2, np.sqrt(2), 256.0)
+    assert relerr(out.cpu().numpy(), g['dense_y']) <= 2e-6
+    x = K.normalize_2nd_moment(t(g['map_z']))
+    for i in range(8):
+        w, b = t(g[f'map_mapping.fc{i}.weight']), t(g[f'map_mapping.fc{i}.bias'])
+        o = torch.empty((3, 64), device=DEV)
+        x = K.dense(x, w, b, o, 0.01 / np.sqrt(64), 0.01, True, 0.2, np.sqrt(2), 256.0)
+    assert relerr(x.cpu().numpy(), g['map_ws'][:, 0]) <= 1e-5
+    # concatenated / strided inputs (styles = affine(cat[w, x_global]))
+    r = np.random.default_rng(3)
+    a, b2, w = r.standard_normal((9, 4, 32)).astype(np.float32), r.standard_normal((9, 64)).astype(np.float32), r.standard_normal((20, 96)).astype(np.float32)
+    o = torch.empty((9, 20), device=DEV)
+    K.dense(t(a)[:, 2], t(w), None, o, 0.3, 1.0, False, x1=t(b2))
+    ref = np.concatenate([a[:, 2], b2], 1) @ w.T * 0.3
+    assert relerr(o.cpu().numpy(), ref) <= 2e-6
+
+
+def test_style_prep():
+    from shgan_b200 import kernels as K
+    r = np.random.default_rng(4)
+    s = (1 + 0.5 * r.standard_normal((5, 128))).astype(np.float32)
+    wsq = r.random((64, 128)).astype(np.float32)
+    s_hat, dc = torch.empty((5, 128), device=DEV), torch.empty((5, 64), device=DEV)
+    K.style_prep(t(s), t(wsq), s_hat, dc, True)
+    sn = s / np.sqrt(np.mean(s.astype(np.float64) ** 2))
+    assert relerr(s_hat.cpu().numpy(), sn) <= 2e-6
+    assert relerr(dc.cpu().numpy(), 1 / np.sqrt((sn ** 2) @ wsq.T + 1e-8)) <= 3e-6
+    K.style_prep(t(s), None, s_hat, None, False, 0.25)
+    assert relerr(s_hat.cpu().numpy(), s * 0.25) <= 1e-7
+
+
+# ---------------------------------------------------------------------------------------------- FIR / pointwise
+def test_fir_nhwc_epilogue_and_parity():
+    from shgan_b200 import kernels as K
+    r = np.random.default_rng(5)
+    f = O.setup_filter([1, 3, 3, 1])
+    x = r.standard_normal((2, 16, 11, 13)).astype(np.float32)          # NCHW
+    skip = r.standard_normal((2, 16, 12, 14)).astype(np.float32)
+    bias = r.standard_normal(16).astype(np.float32)
+    dco = r.random((2, 16)).astype(np.float32) + 0.5
+    nxt = r.random((2, 16)).astype(np.float32) + 0.5
+    nz = r.standard_normal((12, 14)).astype(np.float32)
+    xp = K.nchw_to_planes(t(x))
+    out = K.Planes.empty(2, 12, 14, 16, DEV)
+    of32 = torch.empty((2, 12, 14, 16), device=DEV)
+    strength = torch.tensor(0.3, device=DEV)
+    epi = K.make_epilogue(dcoef=t(dco), noise=t(nz), noise_sn=0, noise_strength=strength, bias=t(bias), act=True, act_alpha=0.2,
+                          act_gain=np.sqrt(2), act_clamp=256.0, skip=K.nchw_to_planes(t(skip)), next_scale=t(nxt), out=out, out_f32=of32)
+    K.fir_nhwc(xp, t(f), 4.0, (2, 2, 2, 2), epi)
+    ref = O.upfirdn2d(x, f, padding=[2, 2, 2, 2], gain=4) * dco[:, :, None, None] + nz[None, None] * 0.3 + bias[None, :, None, None]
+    ref = O.lrelu_agc(ref) + skip
+    assert relerr(K.nhwc_to_nchw_f32(of32).cpu().numpy(), ref) <= 3e-6
+    assert relerr(K.planes_to_nchw(out).cpu().numpy(), ref * nxt[:, :, None, None]) <= 3e-6
+    # fp32 NHWC input + parity-split output
+    xin = torch.from_numpy(x.transpose(0, 2, 3, 1).copy()).to(DEV)
+    ph, pw = 6, 7
+    par = K.Planes.empty(4 * 2, ph, pw, 16, DEV)
+    K.fir_nhwc(xin, t(f), 1.0, (2, 2, 2, 2), K.make_epilogue(out=par), parity_split=True)
+    ref = O.upfirdn2d(x, f, padding=[2, 2, 2, 2])
+    got = K.planes_to_nchw(par).cpu().numpy().reshape(4, 2, 16, ph, pw)
+    for py in range(2):
+        for px in range(2):
+            sub = ref[:, :, py::2, px::2]
+            assert relerr(got[py * 2 + px][:, :, :sub.shape[2], :sub.shape[3]], sub) <= 3e-6
+
+
+def test_fromrgb_and_torgb_combine():
+    from shgan_b200 import kernels as K
+    r = np.random.default_rng(6)
+    x = r.standard_normal((2, 4, 10, 12)).astype(np.float32)
+    w = r.standard_normal((64, 4)).astype(np.float32)
+    b = r.standard_normal(64).astype(np.float32)
+    out = K.fromrgb(t(x), t(w), t(b), 0.5, 0.2, np.sqrt(2), 256.0, K.Planes.empty(2, 10, 12, 64, DEV))
+    ref = O.lrelu_agc(np.einsum('nchw,oc->nohw', x, w * 0.5) + b[None, :, None, None])
+    assert relerr(K.planes_to_nchw(out).cpu().numpy(), ref) <= 3e-6
+    f = O.setup_filter([1, 3, 3, 1])
+    prev = r.standard_normal((2, 3, 5, 6)).astype(np.float32)
+    part = r.standard_normal((2, 10, 12, 3, 4)).astype(np.float32)
+    bias = r.standard_normal(3).astype(np.float32)
+    cx = np.concatenate([(r.random((2, 1, 10, 12)) > 0.5).astype(np.float32) - 0.5, r.uniform(-1, 1, (2, 3, 10, 12)).astype(np.float32)], 1)
+    img = torch.empty((2, 3, 10, 12), device=DEV)
+    comp = torch.empty((2, 3, 10, 12), dtype=torch.uint8, device=DEV)
+    K.torgb_combine(t(prev), t(part), t(bias), t(f), img, comp_x=t(cx), comp_out=comp)
+    ref = O.upsample2d(prev, f) + part[..., :3].sum(3).transpose(0, 3, 1, 2) + bias[None, :, None, None]
+    assert relerr(img.cpu().numpy(), ref) <= 3e-6
+    refc = O.composite_uint8(cx, img.cpu().numpy())
+    assert np.abs(comp.cpu().numpy().astype(int) - refc.astype(int)).max() <= 1
+    assert (comp.cpu().numpy() != refc).mean() < 1e-3
+    img0 = torch.empty((2, 3, 10, 12), device=DEV)
+    K.torgb_combine(None, t(part), t(bias), None, img0)
+    assert relerr(img0.cpu().numpy(), part[..., :3].sum(3).transpose(0, 3, 1, 2) + bias[None, :, None, None]) <= 2e-6
+
+
+# ---------------------------------------------------------------------------------------------- SHU
+def test_shu_golden(golden):
+    from shgan_b200.model_zoo.shgan import SHU
+    g = golden('shu')
+    sd = {k: v for k, v in O.synthetic_state_dict(256, seed=7).items() if k.startswith('encoder.shu')}
+    shu = SHU(32, 32, dfilter_freedom=[2, 3], dfilter_type='piecewise_linear', input_res=64, lowest_res=4)
+    shu.load_state_dict({k[len('encoder.shu.'):]: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    shu = shu.to(DEV)
+    x = rng(500).standard_normal((1, 32, 64, 64)).astype(np.float32)
+    y = shu(t(x))
+    assert sorted(y) == [4, 8, 16, 32, 64]
+    for r in y:
+        ref = g[f'out{r}']
+        assert y[r].shape == ref.shape
+        assert relerr(y[r].cpu().numpy(), ref) <= 2e-5, r
+    # other input resolutions (C5 sweep sizes) and batch > 1 against the oracle
+    for n in (16, 128):
+        shu_n = SHU(32, 32, dfilter_freedom=[2, 3], dfilter_type='piecewise_linear', input_res=n, lowest_res=4)
+        shu_n.load_state_dict(shu.state_dict())
+        shu_n = shu_n.to(DEV)
+        xn = rng(510 + n).standard_normal((1, 32, n, n)).astype(np.float32)
+        yn = shu_n(t(xn))
+        assert relerr(yn[4].cpu().numpy(), g[f'sweep{n}_out4']) <= 2e-5
+        tot = g[f'sweep{n}_out{n}_sum']
+        assert abs(float(yn[n].double().abs().sum()) - tot[1]) <= 1e-4 * tot[1]
+    xb = rng(7).standard_normal((3, 32, 64, 64)).astype(np.float32)
+    yb = shu(t(xb))
+    ref = O.shu_forward(sd, xb)
+    for r in ref:
+        assert relerr(yb[r].cpu().numpy(), ref[r]) <= 2e-5
