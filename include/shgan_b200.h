@@ -101,7 +101,7 @@ typedef struct {
  * mode 0 (ACT): apply `epi`, write planes/fp32/rgb.   mode 1 (RAW): write acc as fp32 NHWC into
  * z[n, oy*zsy+zoy, ox*zsx+zox, o] of a [N,ZH,ZW,Co] tensor (used by the 4 parity passes of the
  * stride-2 transposed convolution).  C and Co must be multiples of 64.  In ACT mode with rgb_w set, the
- * torgb partial sums of each block of `block_n` output channels are written to
+ * torgb partial sums of each block of 32 output channels are written to
  * rgb_out[n,y,x,blk,0..2] (blk < shgan_conv_num_nblocks); shgan_torgb_combine adds them up. */
 typedef struct {
     int num_src;
@@ -118,14 +118,14 @@ typedef struct {
     int mode;
     float* z; int ZH, ZW, zsy, zsx, zoy, zox;
     shgan_epilogue epi;
-    int block_n;                 /* 0 = auto (64/128/256) */
+    int block_n;                 /* GEMM tile width: 0 = auto (widest of 64/128/256 that still fills the SMs) */
     int passes;                  /* 3 = fp32-class (default when 0), 1 = hi*hi only (fast, ~fp16 accuracy) */
     int impl;                    /* 0 = tcgen05 tensor-core kernel (the product path);
                                     1 = fp32 FMA kernel with identical operands/epilogue, kept ONLY as the on-device
                                         cross-check of the tensor-core kernel at full layer sizes (tests) */
 } shgan_conv_desc;
 int shgan_conv_igemm(const shgan_conv_desc* d, void* stream);
-/* number of N-blocks the kernel will use for this Co/block_n (size of the rgb partial axis) */
+/* size of the rgb partial axis: Co / 32 (independent of block_n, kept in the signature for ABI stability) */
 int shgan_conv_num_nblocks(int Co, int block_n);
 
 /* ---- FIR (blur) on NHWC data with the fused pointwise epilogue ---------------------------

@@ -4,8 +4,8 @@
 using namespace shgan;
 
 extern "C" int shgan_conv_num_nblocks(int Co, int block_n) {
-    const int bn = conv_block_n(Co, block_n);
-    return bn > 0 && Co % bn == 0 ? Co / bn : 0;
+    (void)block_n;
+    return Co % CONV_RGB_BLOCK == 0 ? Co / CONV_RGB_BLOCK : 0;
 }
 
 extern "C" int shgan_conv_igemm(const shgan_conv_desc* d, void* stream_) {
@@ -34,9 +34,9 @@ extern "C" int shgan_conv_igemm(const shgan_conv_desc* d, void* stream_) {
     } else {
         if (const char* m = check_epi(d->epi, d->Co)) SHGAN_CHECK(false, m);
     }
-    const int bn = conv_block_n(d->Co, d->block_n);
-    SHGAN_CHECK(bn == 64 || bn == 128 || bn == 256, "block_n must be 0, 64, 128 or 256");
-    SHGAN_CHECK(d->Co % bn == 0, "Co must be a multiple of block_n");
+    SHGAN_CHECK(d->block_n == 0 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256, "block_n must be 0, 64, 128 or 256");
+    SHGAN_CHECK(d->block_n == 0 || d->Co % d->block_n == 0, "Co must be a multiple of block_n");
+    const int bn = d->block_n;
     if (d->N == 0) return 0;
     const ConvGeom g = make_geom(*d);
     const EpiParams epi = d->mode == 0 ? make_epi(d->epi) : EpiParams{};

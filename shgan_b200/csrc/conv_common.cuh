@@ -41,6 +41,9 @@ static inline ConvGeom make_geom(const shgan_conv_desc& d) {
 int launch_conv_simt(const ConvGeom& g, const EpiParams& epi, int block_n, cudaStream_t stream);
 int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream);
 
+// torgb partial sums are produced per block of 32 output channels, independent of the GEMM tile width
+constexpr int CONV_RGB_BLOCK = 32;
+
 static inline int conv_block_n(int Co, int block_n) {
     if (block_n == 0) block_n = Co >= 256 ? 256 : (Co >= 128 ? 128 : 64);
     return block_n;

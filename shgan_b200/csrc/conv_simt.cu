@@ -96,8 +96,7 @@ conv_simt_kernel(ConvGeom g, EpiParams epi, int block_n) {
             float rgb[3] = {0.f, 0.f, 0.f};
             epilogue_apply<8>(epi, acc[i], n, y, x, g.OH, g.OW, g.Co, o0, rgb, pix);
             if (epi.rgb_w) {
-                const int nblk = g.Co / block_n;
-                float* dst = epi.rgb_out + (pix * nblk + o0 / block_n) * 4;
+                float* dst = epi.rgb_out + (pix * (g.Co / CONV_RGB_BLOCK) + o0 / CONV_RGB_BLOCK) * 4;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) atomicAdd(dst + j, rgb[j]);
             }
@@ -108,7 +107,7 @@ conv_simt_kernel(ConvGeom g, EpiParams epi, int block_n) {
 int launch_conv_simt(const ConvGeom& g, const EpiParams& epi, int block_n, cudaStream_t stream) {
     const long long npix = (long long)g.N * g.OH * g.OW;
     if (epi.rgb_w && g.mode == 0)
-        SHGAN_CUDA(cudaMemsetAsync(epi.rgb_out, 0, (size_t)npix * (g.Co / block_n) * 4 * sizeof(float), stream));
+        SHGAN_CUDA(cudaMemsetAsync(epi.rgb_out, 0, (size_t)npix * (g.Co / CONV_RGB_BLOCK) * 4 * sizeof(float), stream));
     dim3 grid((unsigned)ceil_div64(npix, SM_PIX), g.Co / SM_CO);
     conv_simt_kernel<<<grid, 256, 0, stream>>>(g, epi, block_n);
     SHGAN_LAUNCH_CHECK();

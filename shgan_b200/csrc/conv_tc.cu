@@ -13,10 +13,17 @@
 //   and each slab issues hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator (the dropped lo*lo
 //   term is < 2^-22 relative).  passes == 1 issues hi*hi only.
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-//   warps 2-5 = epilogue (tcgen05.ld 32 lanes x 32 columns per instruction -> registers -> fused
-//   demod / noise / bias / lrelu / clamp / skip-add / torgb / next-layer modulation -> split planes).
-//   Two TMEM accumulators (2*BN columns) let the epilogue of tile i overlap the MMAs of tile i+1;
-//   an mbarrier ring of STAGES smem slots decouples TMA from MMA.
+//   warps 4-11 = epilogue (tcgen05.ld 32 lanes x 32 columns per instruction -> registers -> fused
+//   demod / noise / bias / lrelu / clamp / skip-add / torgb / next-layer modulation -> split planes);
+//   epilogue warp w owns TMEM lane quarter (w & 3) and column half (w - 4) >> 2 of the tile;
+//   setmaxnreg moves registers from the producer/MMA warpgroup to the two epilogue warpgroups.
+//   An mbarrier ring of STAGES smem slots decouples TMA from MMA.
+// * Two-level accumulation.  The tensor core truncates (does not round) when it adds into the fp32 TMEM
+//   accumulator, which shows up as a bias that grows linearly with the number of chained MMAs (measured:
+//   2.5e-6 relative after 108 MMAs, 1.5e-5 after 864).  The K loop is therefore cut into chunks of at most
+//   4 (tap, slab) steps; each chunk accumulates in one of the two TMEM accumulators (2*BN columns) while the
+//   epilogue warps drain the other one and add it into fp32 registers with round-to-nearest FADDs.  This
+//   bounds the truncation chain for every layer width and is also what overlaps epilogue and MMA.
 #include "conv_common.cuh"
 
 namespace shgan {
@@ -35,8 +42,14 @@ struct TileInfo {
     int total;
 };
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 384;      // warpgroup 0: warp 0 TMA, warp 1 MMA (2 idle); warpgroups 1-2 (warps 4..11): epilogue
+constexpr int TC_EPI_THREADS = 256;
+// setmaxnreg budget: the CTA is launched with 168 registers/thread (the cap ptxas applies for 384 threads); the
+// re-partition must fit in that pool or setmaxnreg.inc blocks forever: 128*DEC + 256*INC <= 384*168.
+constexpr int TC_REGS_LAUNCH = 168, TC_REGS_DEC = 56, TC_REGS_INC = 224;
+static_assert(128 * TC_REGS_DEC + 256 * TC_REGS_INC <= 384 * TC_REGS_LAUNCH, "setmaxnreg budget exceeds the CTA register pool");
 constexpr int TC_M = 128;       // output pixels per tile == UMMA M
+constexpr int TC_MAX_CHUNK_ITERS = 4;   // (tap, slab) steps chained in one TMEM accumulator = 48 MMAs
 constexpr int TC_KC = 64;       // channels per K slab (= 128 B of fp16 = one swizzle row)
 constexpr int A_BYTES = TC_M * TC_KC * 2;
 
@@ -147,11 +160,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- kernel -------------------------------------------------------------------------------------
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const EpiParams epi, const TileInfo ti,
-               const int passes) {
+               const int passes, const int chunk_iters) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -180,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 128);
+            mbar_init(&tempty_bar[a], TC_EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -195,7 +223,9 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_DEC));
+      if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
@@ -238,39 +268,47 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < ti.total; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int it = 0; it < kiters; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
+                for (int it0 = 0; it0 < kiters; it0 += chunk_iters) {
+                    const int n_it = kiters - it0 < chunk_iters ? kiters - it0 : chunk_iters;
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int it = 0; it < n_it; ++it) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < TC_KC / 16; ++k) {
-                        const uint32_t ko = k * 32;  // 16 fp16 = 32 B inside the 128 B swizzle row
-                        const uint64_t dah = umma_desc_sw128(a_hi + ko), dbh = umma_desc_sw128(b_hi + ko);
-                        umma_f16(d_tmem, dah, dbh, idesc, (it | k) != 0);
-                        if (passes == 3) {
-                            umma_f16(d_tmem, umma_desc_sw128(a_lo + ko), dbh, idesc, 1);
-                            umma_f16(d_tmem, dah, umma_desc_sw128(b_lo + ko), idesc, 1);
+                        for (int k = 0; k < TC_KC / 16; ++k) {
+                            const uint32_t ko = k * 32;  // 16 fp16 = 32 B inside the 128 B swizzle row
+                            const uint64_t dah = umma_desc_sw128(a_hi + ko), dbh = umma_desc_sw128(b_hi + ko);
+                            umma_f16(d_tmem, dah, dbh, idesc, (it | k) != 0);
+                            if (passes == 3) {
+                                umma_f16(d_tmem, umma_desc_sw128(a_lo + ko), dbh, idesc, 1);
+                                umma_f16(d_tmem, dah, umma_desc_sw128(b_lo + ko), idesc, 1);
+                            }
                         }
+                        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&tfull_bar[acc]);        // chunk accumulator complete -> epilogue warps
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
                 }
-                umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
             }
         }
+      }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_INC));
+        // ===================== epilogue (warps 4..11) =====================
+        constexpr int HN = BN / 2;              // columns owned by this thread
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;       // column half of the tile
         const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
         const int tx_i = row & (ti.TW - 1);
         const int ty_i = (row >> ti.tw_log2) & (ti.TH - 1);
         const int tn_i = row >> (ti.tw_log2 + ti.th_log2);
+        const int nchunks = (kiters + chunk_iters - 1) / chunk_iters;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < ti.total; tile += gridDim.x) {
@@ -283,28 +321,37 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
             const bool valid = n < g.N && y < g.OH && x < g.OW;
             const long long pix = ((long long)n * g.OH + y) * g.OW + x;
 
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            float rgb[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
-                if (valid) {
-                    const int o0 = nb * BN + c0;
-                    if (g.mode == 1) raw_store<32>(g, v, n, y, x, o0);
-                    else epilogue_apply<32>(epi, v, n, y, x, g.OH, g.OW, g.Co, o0, rgb, pix);
+            float accv[HN];
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN);
+#pragma unroll
+                for (int p = 0; p < HN / 16; ++p) {
+                    float v[16];
+                    tmem_ld16(taddr + p * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) accv[p * 16 + i] = c == 0 ? v[i] : accv[p * 16 + i] + v[i];
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            if (valid) {
+                float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int p = 0; p < HN / 16; ++p) {
+                    const int o0 = nb * BN + half * HN + p * 16;
+                    if (g.mode == 1) raw_store<16>(g, accv + p * 16, n, y, x, o0);
+                    else epilogue_apply<16>(epi, accv + p * 16, n, y, x, g.OH, g.OW, g.Co, o0, rgb, pix);
+                    if ((p & 1) && g.mode == 0 && epi.rgb_w) {   // one torgb partial per CONV_RGB_BLOCK = 32 channels
+                        float* dst = epi.rgb_out + (pix * (g.Co / CONV_RGB_BLOCK) + (o0 - 16) / CONV_RGB_BLOCK) * 4;
+                        *reinterpret_cast<float4*>(dst) = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+                        rgb[0] = rgb[1] = rgb[2] = 0.f;
+                    }
                 }
             }
-            if (valid && g.mode == 0 && epi.rgb_w) {
-                float* dst = epi.rgb_out + (pix * ti.nblk + nb) * 4;
-                *reinterpret_cast<float4*>(dst) = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
-            }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
     }
 
@@ -371,15 +418,17 @@ static int launch_bn(const ConvTmaps& maps, const ConvGeom& g, const EpiParams& 
         attr_set = true;
     }
     const int grid = ti.total < num_sms ? ti.total : num_sms;
-    conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, g, epi, ti, passes);
+    // two-level accumulation: at most TC_MAX_CHUNK_ITERS (tap, slab) steps are chained inside one TMEM accumulator
+    const int kiters = g.ntaps * (g.C / TC_KC);
+    const int nchunks = ceil_div(kiters, TC_MAX_CHUNK_ITERS);
+    const int chunk_iters = ceil_div(kiters, nchunks);
+    conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, g, epi, ti, passes, chunk_iters);
     SHGAN_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream) {
     SHGAN_CHECK(g.C % TC_KC == 0, "C must be a multiple of 64 for the tensor-core path");
-    SHGAN_CHECK(block_n == 64 || block_n == 128 || block_n == 256, "block_n must be 64, 128 or 256");
-    SHGAN_CHECK(g.Co % block_n == 0, "Co must be a multiple of block_n");
     SHGAN_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
     TileInfo ti;
     ti.TW = pow2_ceil(g.OW) < 16 ? pow2_ceil(g.OW) : 16;
@@ -391,6 +440,16 @@ int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int pas
     ti.tiles_x = ceil_div(g.OW, ti.TW);
     ti.tiles_y = ceil_div(g.OH, ti.TH);
     ti.tiles_n = ceil_div(g.N, ti.TN);
+    if (block_n == 0) {
+        // widest tile the layer allows (least operand re-fetch), narrowed while the grid cannot fill the SMs:
+        // small-resolution layers are bound by the serial K loop of a tile, not by bandwidth
+        int dev = 0, num_sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        block_n = conv_block_n(g.Co, 0);
+        const long long mt = (long long)ti.tiles_x * ti.tiles_y * ti.tiles_n;
+        while (block_n > 64 && mt * (g.Co / block_n) < num_sms) block_n >>= 1;
+    }
+    SHGAN_CHECK(g.Co % block_n == 0, "Co must be a multiple of block_n");
     ti.nblk = g.Co / block_n;
     const long long total = (long long)ti.tiles_x * ti.tiles_y * ti.tiles_n * ti.nblk;
     SHGAN_CHECK(total <= INT32_MAX, "too many tiles");

@@ -140,7 +140,7 @@ extern "C" int shgan_upfirdn2d_fwd(const float* x, const float* f, float* y, int
                                    int pady1, int flip, float gain, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     // argument validation mirrors the TORCH_CHECKs of upfirdn2d.cpp:19-36
-    SHGAN_CHECK(x && f && y, "null pointer");
+    SHGAN_CHECK(f && ((x && y) || N == 0 || C == 0), "null pointer");
     SHGAN_CHECK(N >= 0 && C >= 0 && H >= 1 && W >= 1, "bad input size");
     SHGAN_CHECK(fH >= 1 && fW >= 1, "f must be at least 1x1");
     SHGAN_CHECK(upx >= 1 && upy >= 1, "upsampling factor must be at least 1");

@@ -54,8 +54,9 @@ def _apply_epi(acc, e, block_n, parity_split=False):
         v = v + e['skip'].float()
     if e['rgb_w'] is not None:
         t = v * e['rgb_style'][:, None, None, :]
-        nblk = co // block_n
-        part = torch.einsum('nyxbc,jbc->nyxbj', t.reshape(n, oh, ow, nblk, block_n), e['rgb_w'].reshape(3, nblk, block_n))
+        rb = 32                               # partial sums per block of 32 channels (include/shgan_b200.h)
+        nblk = co // rb
+        part = torch.einsum('nyxbc,jbc->nyxbj', t.reshape(n, oh, ow, nblk, rb), e['rgb_w'].reshape(3, nblk, rb))
         e['rgb_out'].zero_()
         e['rgb_out'][..., :3] = part
     if e['out_f32'] is not None:
@@ -82,7 +83,7 @@ def _block_n(co, block_n=0):
 
 
 def conv_num_nblocks(co, block_n=0):
-    return co // _block_n(co, block_n)
+    return co // 32
 
 
 def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0):

@@ -148,9 +148,12 @@ def test_fir_nhwc_epilogue_and_parity():
     out = K.Planes.empty(2, 12, 14, 16, DEV)
     of32 = torch.empty((2, 12, 14, 16), device=DEV)
     strength = torch.tensor(0.3, device=DEV)
-    epi = K.make_epilogue(dcoef=t(dco), noise=t(nz), noise_sn=0, noise_strength=strength, bias=t(bias), act=True, act_alpha=0.2,
-                          act_gain=np.sqrt(2), act_clamp=256.0, skip=K.nchw_to_planes(t(skip)), next_scale=t(nxt), out=out, out_f32=of32)
-    K.fir_nhwc(xp, t(f), 4.0, (2, 2, 2, 2), epi)
+    # the epilogue struct holds raw device pointers: keep every operand alive until the launch has been issued
+    ops_ = dict(dcoef=t(dco), noise=t(nz), bias=t(bias), skip=K.nchw_to_planes(t(skip)), next_scale=t(nxt), f=t(f))
+    epi = K.make_epilogue(dcoef=ops_['dcoef'], noise=ops_['noise'], noise_sn=0, noise_strength=strength, bias=ops_['bias'], act=True,
+                          act_alpha=0.2, act_gain=np.sqrt(2), act_clamp=256.0, skip=ops_['skip'], next_scale=ops_['next_scale'],
+                          out=out, out_f32=of32)
+    K.fir_nhwc(xp, ops_['f'], 4.0, (2, 2, 2, 2), epi)
     ref = O.upfirdn2d(x, f, padding=[2, 2, 2, 2], gain=4) * dco[:, :, None, None] + nz[None, None] * 0.3 + bias[None, :, None, None]
     ref = O.lrelu_agc(ref) + skip
     assert relerr(K.nhwc_to_nchw_f32(of32).cpu().numpy(), ref) <= 3e-6

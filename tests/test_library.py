@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert sorted(_lib.SIGNATURES) == decl                      # the ctypes binding covers exactly the header
     loaded = _lib.load()
     assert loaded.shgan_abi_version() == _lib.ABI_VERSION
-    assert loaded.shgan_conv_num_nblocks(512, 0) == 2 and loaded.shgan_conv_num_nblocks(64, 0) == 1
+    assert loaded.shgan_conv_num_nblocks(512, 0) == 16 and loaded.shgan_conv_num_nblocks(64, 0) == 2
     assert loaded.shgan_shu_workspace_bytes(2, 32, 64) == 2 * 2 * 64 * 64 * 33 * 4
     # struct layouts the binding assumes
     assert ctypes.sizeof(_lib.Epilogue) % 8 == 0 and ctypes.sizeof(_lib.ConvDesc) % 8 == 0
