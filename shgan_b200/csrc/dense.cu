@@ -3,7 +3,8 @@
 // Batch sizes on this path are tiny (B <= 32 per GPU), so every dense layer is a weight-streaming
 // GEMV-like problem bounded by reading W once from HBM: one warp owns one output feature, streams
 // its weight row with 128-bit loads and keeps up to 8 batch accumulators in registers; the input
-// rows (a few hundred KB at most) are served by L1/L2.
+// rows (a few hundred KB at most) are served by L1/L2; DU independent weight loads per lane keep enough bytes in flight
+// to stream the row at HBM speed instead of paying one DRAM latency per 512 B.
 //   shgan_dense_fwd            <- dense.forward (torch.addmm), lib/model_zoo/stylegan.py:87-98
 //   shgan_normalize_2nd_moment <- normalize_2nd_moment, stylegan.py:343-344
 //   shgan_style_prep           <- the style / demodulation arithmetic of modulated_conv2d, stylegan.py:145-155
@@ -11,7 +12,7 @@
 
 namespace shgan {
 
-constexpr int DB = 8;  // batch rows per pass
+constexpr int DCH = 512;  // input features per staged chunk: 4 x 128-bit weight loads in flight per lane
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -19,40 +20,60 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Block = 8 warps = 8 output features; the NB input rows of the current chunk are staged once per block in shared
+// memory (coalesced), each warp streams its own weight-row chunk from HBM with 4 independent 128-bit loads per lane.
+template <int NB>
 __global__ void __launch_bounds__(256)
 dense_kernel(const float* __restrict__ x0, long long x0_stride, int I0, const float* __restrict__ x1, long long x1_stride,
              const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y, long long y_stride, int B,
              int I, int O, float wgain, float bgain, int act, float act_alpha, float act_gain, float act_clamp) {
+    __shared__ __align__(16) float xs[NB][DCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o = blockIdx.x * 8 + warp;
-    if (o >= O) return;
-    const float* wr = w + (long long)o * I;
-    for (int b0 = 0; b0 < B; b0 += DB) {
-        float acc[DB];
+    const bool live = o < O;
+    const float* wr = w + (long long)(live ? o : 0) * I;
+    for (int b0 = 0; b0 < B; b0 += NB) {
+        float acc[NB];
 #pragma unroll
-        for (int j = 0; j < DB; ++j) acc[j] = 0.f;
-        for (int i = lane * 4; i < I; i += 128) {
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + i));
-            const bool first = i < I0;  // I0 is a multiple of 4, so a quad never straddles the two inputs
+        for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+        for (int ic = 0; ic < I; ic += DCH) {
+            float4 wv[DCH / 128];
 #pragma unroll
-            for (int j = 0; j < DB; ++j) {
-                if (b0 + j < B) {
-                    const float* xp = first ? x0 + (long long)(b0 + j) * x0_stride + i
-                                            : x1 + (long long)(b0 + j) * x1_stride + (i - I0);
-                    const float4 xv = __ldg(reinterpret_cast<const float4*>(xp));
-                    acc[j] = fmaf(xv.x, wv.x, acc[j]);
-                    acc[j] = fmaf(xv.y, wv.y, acc[j]);
-                    acc[j] = fmaf(xv.z, wv.z, acc[j]);
-                    acc[j] = fmaf(xv.w, wv.w, acc[j]);
+            for (int u = 0; u < DCH / 128; ++u) {
+                const int i = ic + u * 128 + lane * 4;
+                wv[u] = (live && i < I) ? __ldg(reinterpret_cast<const float4*>(wr + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();   // previous chunk fully consumed
+            for (int q = threadIdx.x; q < NB * (DCH / 4); q += 256) {
+                const int j = q / (DCH / 4), i = ic + (q % (DCH / 4)) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b0 + j < B && i < I) {
+                    // I0 is a multiple of 4, so a quad never straddles the two concatenated inputs
+                    const float* xp = i < I0 ? x0 + (long long)(b0 + j) * x0_stride + i
+                                             : x1 + (long long)(b0 + j) * x1_stride + (i - I0);
+                    v = __ldg(reinterpret_cast<const float4*>(xp));
+                }
+                *reinterpret_cast<float4*>(&xs[j][(q % (DCH / 4)) * 4]) = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < DCH / 128; ++u) {
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[j][u * 128 + lane * 4]);
+                    acc[j] = fmaf(xv.x, wv[u].x, acc[j]);
+                    acc[j] = fmaf(xv.y, wv[u].y, acc[j]);
+                    acc[j] = fmaf(xv.z, wv[u].z, acc[j]);
+                    acc[j] = fmaf(xv.w, wv[u].w, acc[j]);
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < DB; ++j) acc[j] = warp_sum(acc[j]);
-        if (lane == 0) {
+        for (int j = 0; j < NB; ++j) acc[j] = warp_sum(acc[j]);
+        if (lane == 0 && live) {
             const float bv = bias ? __ldg(bias + o) * bgain : 0.f;
 #pragma unroll
-            for (int j = 0; j < DB; ++j) {
+            for (int j = 0; j < NB; ++j) {
                 if (b0 + j < B) {
                     float v = acc[j] * wgain + bv;
                     if (act) v = lrelu_agc(v, act_alpha, act_gain, act_clamp);
@@ -131,8 +152,12 @@ extern "C" int shgan_dense_fwd(const float* x0, int64_t x0_stride, int I0, const
     SHGAN_CHECK(I % 4 == 0 && I0 % 4 == 0 && x0_stride % 4 == 0 && x1_stride % 4 == 0, "feature counts/strides must be multiples of 4");
     SHGAN_CHECK(I0 >= 0 && I0 <= I && (I0 == I || x1), "second input missing");
     if (B == 0) return 0;
-    dense_kernel<<<ceil_div(O, 8), 256, 0, (cudaStream_t)stream>>>(x0, x0_stride, I0, x1, x1_stride, w, bias, y, y_stride, B, I,
-                                                                   O, wgain, bgain, act, act_alpha, act_gain, act_clamp);
+    if (B <= 8)
+        dense_kernel<8><<<ceil_div(O, 8), 256, 0, (cudaStream_t)stream>>>(x0, x0_stride, I0, x1, x1_stride, w, bias, y, y_stride,
+                                                                          B, I, O, wgain, bgain, act, act_alpha, act_gain, act_clamp);
+    else
+        dense_kernel<16><<<ceil_div(O, 8), 256, 0, (cudaStream_t)stream>>>(x0, x0_stride, I0, x1, x1_stride, w, bias, y, y_stride,
+                                                                           B, I, O, wgain, bgain, act, act_alpha, act_gain, act_clamp);
     SHGAN_LAUNCH_CHECK();
     return 0;
 }

@@ -18,9 +18,9 @@ __global__ void __launch_bounds__(256)
 fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float wgain,
                float act_alpha, float act_gain, float act_clamp, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                int N, int Ci, int Co, int HW) {
-    __shared__ float s_w[FRGB_MAX_CO * FRGB_MAX_CI];
-    __shared__ float s_b[FRGB_MAX_CO];
-    for (int i = threadIdx.x; i < Co * Ci; i += blockDim.x) s_w[i] = w[i] * wgain;
+    __shared__ __align__(16) float s_w[FRGB_MAX_CI * FRGB_MAX_CO];   // transposed [i][o]: a thread's 8 outputs are 2 x LDS.128,
+    __shared__ __align__(16) float s_b[FRGB_MAX_CO];                 // conflict-free across the warp's 8 channel groups
+    for (int i = threadIdx.x; i < Co * Ci; i += blockDim.x) s_w[(i % Ci) * Co + i / Ci] = w[i] * wgain;
     for (int i = threadIdx.x; i < Co; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
     __syncthreads();
     const int cgs = Co / 8;
@@ -35,15 +35,21 @@ fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
 #pragma unroll
         for (int i = 0; i < FRGB_MAX_CI; ++i) xin[i] = i < Ci ? __ldg(x + ((long long)n * Ci + i) * HW + p) : 0.f;
         float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int o = cg * 8 + j;
-            float a = 0.f;
-#pragma unroll
-            for (int i = 0; i < FRGB_MAX_CI; ++i)
-                if (i < Ci) a = fmaf(xin[i], s_w[o * Ci + i], a);
-            v[j] = lrelu_agc(a + s_b[o], act_alpha, act_gain, act_clamp);
+        {
+            const float4 b0 = *reinterpret_cast<const float4*>(s_b + cg * 8), b1 = *reinterpret_cast<const float4*>(s_b + cg * 8 + 4);
+            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
         }
+#pragma unroll
+        for (int i = 0; i < FRGB_MAX_CI; ++i) {
+            if (i < Ci) {
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + i * Co + cg * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + i * Co + cg * 8 + 4);
+                v[0] = fmaf(xin[i], w0.x, v[0]); v[1] = fmaf(xin[i], w0.y, v[1]); v[2] = fmaf(xin[i], w0.z, v[2]); v[3] = fmaf(xin[i], w0.w, v[3]);
+                v[4] = fmaf(xin[i], w1.x, v[4]); v[5] = fmaf(xin[i], w1.y, v[5]); v[6] = fmaf(xin[i], w1.z, v[6]); v[7] = fmaf(xin[i], w1.w, v[7]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = lrelu_agc(v[j], act_alpha, act_gain, act_clamp);
         store_planes8(out_hi, out_lo, pix * Co + cg * 8, v);
     }
 }
