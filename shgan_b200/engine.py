@@ -43,12 +43,14 @@ class GeneratorEngine:
     """passes: 3 = fp32-class split-precision tensor-core convolutions (parity mode), 1 = single fp16 pass.
     impl: 0 = tcgen05 kernel (product), 1 = fp32 FMA cross-check kernel (tests only)."""
 
-    def __init__(self, G, passes=3, impl=0):
+    def __init__(self, G, passes=3, impl=0, graphs=True):
         self.G = G
         self.passes = passes
         self.impl = impl
+        self.graphs = graphs      # replay the ~170 launches of a forward as one CUDA graph per (shape, mode)
         self._sig = None
         self._buf = {}
+        self._graphs = {}
 
     # ---- parameter packing ---------------------------------------------------------------------
     def _signature(self):
@@ -160,6 +162,7 @@ class GeneratorEngine:
         if self._sig is None or self._sig != self._signature():
             self.refresh()
             self._buf = {}
+            self._graphs = {}     # captured graphs reference the old packed operands
 
     # ---- buffers --------------------------------------------------------------------------------------
     def _planes(self, name, n, h, w, c):
@@ -332,8 +335,38 @@ class GeneratorEngine:
 
     def forward(self, x, z, noise_mode='random', composite=False):
         """comodgan.Generator.forward (comodgan.py:449-481).  composite=True additionally returns the eval loop's
-        uint8 composite (shgan_default.py:257-262) fused into the last kernel."""
+        uint8 composite (shgan_default.py:257-262) fused into the last kernel.  With `graphs` the launch sequence is
+        captured once per (shape, noise_mode, composite, passes, impl) and replayed; torch's graph-safe Philox keeps
+        noise_mode='random' drawing fresh noise on every replay.  The returned tensors are engine-owned buffers."""
         self._ensure()
+        if not (self.graphs and x.is_cuda):
+            return self._forward_eager(x, z, noise_mode, composite)
+        key = (tuple(x.shape), tuple(z.shape), noise_mode, composite, self.passes, self.impl)
+        entry = self._graphs.get(key)
+        if entry is None:
+            xs = x.detach().contiguous().float().clone()
+            zs = z.detach().contiguous().float().clone()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            rng = torch.cuda.get_rng_state(self.dev)
+            with torch.cuda.stream(side):      # warm-up: allocates the persistent buffers, loads the kernels
+                self._forward_eager(xs, zs, noise_mode, composite)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            torch.cuda.set_rng_state(rng, self.dev)   # the warm-up must not consume the caller's random stream
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_eager(xs, zs, noise_mode, composite)
+            entry = (graph, xs, zs, out)
+            self._graphs[key] = entry
+        graph, xs, zs, out = entry
+        xs.copy_(x, non_blocking=True)
+        zs.copy_(z, non_blocking=True)
+        graph.replay()
+        return out
+
+    def _forward_eager(self, x, z, noise_mode='random', composite=False):
         w = self.mapping(z)
         num_ws = self.G.num_ws
         ws = w.unsqueeze(1).expand(w.shape[0], num_ws, w.shape[1])

@@ -221,7 +221,7 @@ class Generator(Generator_StyleGan):
         for sub in (self.encoder, self.synthesis):
             sub.__dict__['_owner'] = weakref.ref(self)
 
-    def engine(self, passes=None, impl=None):
+    def engine(self, passes=None, impl=None, graphs=None):
         eng = self.__dict__.get('_engine_obj')
         if eng is None:
             eng = GeneratorEngine(self)
@@ -230,6 +230,8 @@ class Generator(Generator_StyleGan):
             eng.passes = passes
         if impl is not None:
             eng.impl = impl
+        if graphs is not None:
+            eng.graphs = graphs
         return eng
 
     def __deepcopy__(self, memo):

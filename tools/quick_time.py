@@ -21,11 +21,12 @@ def main():
     ap.add_argument('--impl', type=int, default=0)
     ap.add_argument('--passes', type=int, default=3)
     ap.add_argument('--iters', type=int, default=5)
+    ap.add_argument('--graphs', type=int, default=1)
     ap.add_argument('--layers', action='store_true', help='per-call timing via launch blocking events')
     a = ap.parse_args()
     sd = O.synthetic_state_dict(a.res, seed=0)
     G = H.build_generator(a.res, sd, device='cuda')
-    G.engine(passes=a.passes, impl=a.impl)
+    G.engine(passes=a.passes, impl=a.impl, graphs=bool(a.graphs) and not a.layers)
     x, z = O.synthetic_inputs(a.batch, a.res, seed=0)
     x, z = torch.from_numpy(x).cuda(), torch.from_numpy(z).cuda()
     for _ in range(2):
@@ -73,7 +74,7 @@ def main():
         ts.append(s.elapsed_time(e))
     ms = min(ts)
     flop = {512: 238.785e9, 256: 180.635e9}.get(a.res, 0) * a.batch
-    print(f'res {a.res} batch {a.batch} impl {a.impl} passes {a.passes}: best {ms:.3f} ms median {sorted(ts)[len(ts)//2]:.3f} ms '
+    print(f'res {a.res} batch {a.batch} impl {a.impl} passes {a.passes} graphs {a.graphs}: best {ms:.3f} ms median {sorted(ts)[len(ts)//2]:.3f} ms '
           f'-> {a.batch / ms * 1e3:.1f} img/s, {flop / ms / 1e9:.1f} algorithmic TFLOP/s')
 
 
