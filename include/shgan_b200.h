@@ -134,8 +134,10 @@ int shgan_conv_num_nblocks(int Co, int block_n);
  * in: either fp32 NHWC `in_f32` or split planes in_hi/in_lo, [N,IH,IW,C].
  * out[n,y,x,c] = gain * sum_{i<fH,j<fW} f[i,j] * in[n, y+i-pad_y0, x+j-pad_x0, c]  (f already flipped
  * as needed by the caller), OH = IH+pad_y0+pad_y1-fH+1, then `epi` (Co == C).
- * parity_split != 0: out planes are written de-interleaved as 4 tensors [N,PH,PW,C], plane
- * q=(y&1)*2+(x&1) at out_hi + q*N*PH*PW*C, element (y>>1, x>>1); PH=(OH+1)/2, PW=(OW+1)/2. */
+ * parity_split == 1: out planes are written de-interleaved as 4 tensors [N,PH,PW,C], plane
+ * q=(y&1)*2+(x&1) at out_hi + q*N*PH*PW*C, element (y>>1, x>>1); PH=(OH+1)/2, PW=(OW+1)/2.
+ * parity_split == 2: only the even/even samples are kept, out planes [N,PH,PW,C] (= upfirdn2d with down=2:
+ * the discriminator's skip path, conv2d_resample.py:105-108). */
 int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void* in_lo,
                    const float* f, int fH, int fW, float gain,
                    int N, int C, int IH, int IW, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
@@ -154,6 +156,11 @@ int shgan_fromrgb(const float* x, const float* w /*[Co,Ci]*/, const float* bias,
 int shgan_torgb_combine(const float* img_prev, const float* rgb_partial, int n_blocks, const float* bias,
                         const float* f /*[4,4]*/, float* img_out, int N, int H, int W,
                         const float* comp_x /*[N,4,H,W] or NULL*/, uint8_t* comp_out, void* stream);
+
+/* minibatch_std_layer (num_channels = 1) fused with the channel concat of lib/model_zoo/stylegan.py:686-705:
+ * out planes [N,H,W,C_out] = [ in planes [N,H,W,C] | std statistic of the sample's group | zeros ]. */
+int shgan_mbstd_append(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int N, int H, int W, int C,
+                       int C_out, int group_size, void* stream);
 
 /* ---- dense / styles ------------------------------------------------------------------------
  * y[b,o] = act( (sum_i x[b,i] w[o,i]) * wgain + bias[o]*bgain )   replaces dense.forward

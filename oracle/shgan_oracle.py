@@ -607,6 +607,97 @@ def generator(sd, x, z, resolution, noise_mode='const', noises=None, with_shu=Tr
     return img
 
 
+# ----------------------------------------------------------------------------------------
+# discriminator  (stylegan.py:624-838; comodgan.py:483-485 registers it as comodgan_discriminator)
+# ----------------------------------------------------------------------------------------
+
+def minibatch_std(x, group_size=4, num_channels=1):
+    """stylegan.py:686-705: std over groups of `group_size` samples, averaged over channels and pixels, appended
+    as `num_channels` extra feature maps."""
+    n, c, h, w = x.shape
+    g = min(group_size, n) if group_size is not None else n
+    f = num_channels
+    cc = c // f
+    y = x.reshape(g, -1, f, cc, h, w)
+    y = y - y.mean(axis=0)
+    y = np.square(y).mean(axis=0)
+    y = np.sqrt(y + x.dtype.type(1e-8))
+    y = y.mean(axis=(2, 3, 4))
+    y = y.reshape(-1, f, 1, 1)
+    y = np.tile(y, (g, 1, h, w))
+    return np.concatenate([x, y.astype(x.dtype)], axis=1)
+
+
+def discriminator(sd, img, resolution, mbstd_group_size=4, mbstd_c_n=1, prefix='', return_intermediates=False):
+    """Discriminator.forward (stylegan.py:828-838) with discrim_block.forward (:658-684, reslink=True) and
+    discrim_epilogue.forward (:743-755), c_dim == 0."""
+    log2 = int(np.log2(resolution))
+    res_list = [2 ** i for i in range(log2, 1, -1)]
+    p0 = prefix
+    x = None
+    inter = {}
+    for idx, r in enumerate(res_list[:-1]):
+        p = f'{p0}b{r}'
+        if idx == 0:
+            x = conv2d_layer(sd, p + '.fromrgb', img)
+        y = conv2d_layer(sd, p + '.skip', x, down=2, act=False, gain=np.sqrt(0.5))
+        x = conv2d_layer(sd, p + '.conv0', x)
+        x = conv2d_layer(sd, p + '.conv1', x, down=2, gain=np.sqrt(0.5))
+        x = y + x
+        inter[r // 2] = x
+    x = minibatch_std(x, mbstd_group_size, mbstd_c_n) if mbstd_c_n > 0 else x
+    x = conv2d_layer(sd, f'{p0}b4.conv', x)
+    x = dense(x.reshape(x.shape[0], -1), sd[f'{p0}b4.fc.weight'], sd[f'{p0}b4.fc.bias'], act=True)
+    x = dense(x, sd[f'{p0}b4.out.weight'], sd[f'{p0}b4.out.bias'])
+    if return_intermediates:
+        return x, inter
+    return x
+
+
+def discriminator_state_dict_spec(resolution, ic_n=4, ch_base=32768, ch_max=512, mbstd_c_n=1):
+    """Key -> shape of comodgan_discriminator in registration order."""
+    log2 = int(np.log2(resolution))
+    C = lambda r: channels(r, ch_base, ch_max)
+    spec = []
+    for i in range(log2, 2, -1):
+        r = 2 ** i
+        c, cn = C(r), C(r // 2)
+        spec.append((f'b{r}.resample_filter', (4, 4)))
+        if i == log2:
+            spec.append((f'b{r}.fromrgb.weight', (c, ic_n, 1, 1)))
+            spec.append((f'b{r}.fromrgb.bias', (c,)))
+        spec.append((f'b{r}.conv0.weight', (c, c, 3, 3)))
+        spec.append((f'b{r}.conv0.bias', (c,)))
+        spec.append((f'b{r}.conv1.weight', (cn, c, 3, 3)))
+        spec.append((f'b{r}.conv1.bias', (cn,)))
+        spec.append((f'b{r}.conv1.resample_filter', (4, 4)))
+        spec.append((f'b{r}.skip.weight', (cn, c, 1, 1)))
+        spec.append((f'b{r}.skip.resample_filter', (4, 4)))
+    c4 = C(4)
+    spec.append(('b4.conv.weight', (c4, c4 + mbstd_c_n, 3, 3)))
+    spec.append(('b4.conv.bias', (c4,)))
+    spec.append(('b4.fc.weight', (c4, c4 * 16)))
+    spec.append(('b4.fc.bias', (c4,)))
+    spec.append(('b4.out.weight', (1, c4)))
+    spec.append(('b4.out.bias', (1,)))
+    return spec
+
+
+def synthetic_discriminator_state_dict(resolution, seed=0, **kw):
+    sd = {}
+    f = setup_filter([1, 3, 3, 1])
+    for key, shape in discriminator_state_dict_spec(resolution, **kw):
+        rng = np.random.Generator(np.random.PCG64(_key_seed(seed, 'D/' + key)))
+        if key.endswith('resample_filter'):
+            v = f.copy()
+        elif key.endswith('.bias'):
+            v = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        else:
+            v = rng.standard_normal(shape).astype(np.float32)
+        sd[key] = np.ascontiguousarray(v)
+    return sd
+
+
 def composite_uint8(x, img):
     """run_generator, lib/experiments/shgan_default.py:257-262."""
     m = x[:, 0:1] + x.dtype.type(0.5)

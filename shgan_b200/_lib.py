@@ -58,6 +58,7 @@ SIGNATURES = {
     'shgan_fir_nhwc': (i32, [fp, vp, vp, fp, i32, i32, f32] + [i32] * 8 + [C.POINTER(Epilogue), i32, vp]),
     'shgan_fromrgb': (i32, [fp, fp, fp, f32, f32, f32, f32, vp, vp] + [i32] * 5 + [vp]),
     'shgan_torgb_combine': (i32, [fp, fp, i32, fp, fp, fp, i32, i32, i32, fp, vp, vp]),
+    'shgan_mbstd_append': (i32, [vp, vp, vp, vp] + [i32] * 6 + [vp]),
     'shgan_dense_fwd': (i32, [fp, i64, i32, fp, i64, fp, fp, fp, i64, i32, i32, i32, f32, f32, i32, f32, f32, f32, vp]),
     'shgan_normalize_2nd_moment': (i32, [fp, fp, i32, i32, vp]),
     'shgan_style_prep': (i32, [fp, fp, fp, fp, i32, i32, i32, i32, f32, vp]),

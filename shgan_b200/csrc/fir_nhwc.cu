@@ -104,11 +104,13 @@ fir4x4_nhwc_kernel(const float* __restrict__ in_f32, const __half* __restrict__ 
 #pragma unroll
                 for (int ox = 0; ox < FIR_SX; ++ox) {
                     const int x = x0 + ox;
-                    if (x < OW) {
+                    if (x < OW && !(parity_split == 2 && ((yo | x) & 1))) {
                         long long out_pix = ((long long)n * OH + yo) * OW + x;
-                        if (parity_split) {
+                        if (parity_split == 1) {
                             const int q = (yo & 1) * 2 + (x & 1);
                             out_pix = (long long)q * N * PH * PW + ((long long)n * PH + (yo >> 1)) * PW + (x >> 1);
+                        } else if (parity_split == 2) {
+                            out_pix = ((long long)n * PH + (yo >> 1)) * PW + (x >> 1);
                         }
                         float rgb[3] = {0.f, 0.f, 0.f};
                         epilogue_apply<8>(epi, acc[0][ox], n, yo, x, OH, OW, C, c0, rgb, out_pix);
@@ -249,11 +251,13 @@ fir4x4_tma_kernel(const __grid_constant__ FirMaps maps, const float* __restrict_
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc[sl][j] = fmaf(row[fx][j], fk[FIR_T - 1 - sl][fx], acc[sl][j]);
             const int yo = y0 + jrow - (FIR_T - 1);
-            if (jrow >= FIR_T - 1 && yo < OH && x < OW) {
+            if (jrow >= FIR_T - 1 && yo < OH && x < OW && !(parity_split == 2 && ((yo | x) & 1))) {
                 long long out_pix = ((long long)n * OH + yo) * OW + x;
-                if (parity_split) {
+                if (parity_split == 1) {
                     const int q = (yo & 1) * 2 + (x & 1);
                     out_pix = (long long)q * N * PH * PW + ((long long)n * PH + (yo >> 1)) * PW + (x >> 1);
+                } else if (parity_split == 2) {
+                    out_pix = ((long long)n * PH + (yo >> 1)) * PW + (x >> 1);
                 }
                 float rgb[3] = {0.f, 0.f, 0.f};
                 epilogue_apply<8>(epi, acc[0], n, yo, x, OH, OW, C, c0, rgb, out_pix);
@@ -285,7 +289,8 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
     SHGAN_CHECK(OH >= 1 && OW >= 1, "output must be at least 1x1");
     if (const char* m = check_epi(*epi_, C)) SHGAN_CHECK(false, m);
     SHGAN_CHECK(!epi_->rgb_w, "fused torgb is not available in the FIR epilogue");
-    SHGAN_CHECK(!parity_split || (!epi_->out_f32 && !epi_->skip_hi), "parity_split supports plane output only");
+    SHGAN_CHECK(parity_split >= 0 && parity_split <= 2, "parity_split must be 0, 1 or 2");
+    SHGAN_CHECK(!parity_split || (!epi_->out_f32 && !epi_->skip_hi && !epi_->noise), "parity_split supports plane output only");
     SHGAN_CHECK((long long)N * C * ((long long)OH + 1) * (OW + 1) <= INT32_MAX, "tensor is too large");
     if (N == 0) return 0;
     EpiParams epi = make_epi(*epi_);

@@ -120,9 +120,73 @@ torgb_combine_kernel(const float* __restrict__ img_prev, const float* __restrict
     }
 }
 
+// minibatch_std_layer (stylegan.py:686-705) with num_channels == 1, fused with the channel concat: one CTA per group
+// of G samples {g*(N/G) + grp}: stat = mean over (c,y,x) of sqrt(var_over_group + 1e-8); the output planes carry the
+// C input channels, the statistic in channel C, zeros up to C_out (channel padding for the tensor-core conv).
+__global__ void __launch_bounds__(256)
+mbstd_append_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
+                    __half* __restrict__ out_lo, int N, int G, int HW, int C, int C_out) {
+    __shared__ float red[8];
+    __shared__ float s_stat;
+    const int groups = N / G, grp = blockIdx.x;
+    const int E = HW * C;
+    float sum = 0.f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        float v[8];
+        float m = 0.f;
+        for (int g = 0; g < G; ++g) {
+            const long long i = (long long)(g * groups + grp) * E + e;
+            v[g] = __half2float(in_hi[i]) + __half2float(in_lo[i]);
+            m += v[g];
+        }
+        m /= (float)G;
+        float var = 0.f;
+        for (int g = 0; g < G; ++g) var += (v[g] - m) * (v[g] - m);
+        sum += sqrtf(var / (float)G + 1e-8f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        s_stat = t / (float)E;
+    }
+    __syncthreads();
+    const float stat = s_stat;
+    for (int g = 0; g < G; ++g) {
+        const long long n = g * groups + grp;
+        for (int e = threadIdx.x; e < HW * C_out; e += blockDim.x) {
+            const int p = e / C_out, c = e - p * C_out;
+            __half h, l;
+            if (c < C) {
+                h = in_hi[(n * HW + p) * C + c];
+                l = in_lo[(n * HW + p) * C + c];
+            } else {
+                split_f32(c == C ? stat : 0.f, h, l);
+            }
+            out_hi[(n * HW + p) * C_out + c] = h;
+            out_lo[(n * HW + p) * C_out + c] = l;
+        }
+    }
+}
+
 }  // namespace shgan
 
 using namespace shgan;
+
+extern "C" int shgan_mbstd_append(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int N, int H, int W, int C,
+                                  int C_out, int group_size, void* stream) {
+    SHGAN_CHECK(in_hi && in_lo && out_hi && out_lo, "null pointer");
+    SHGAN_CHECK(N >= 1 && H >= 1 && W >= 1 && C >= 1 && C_out > C, "bad sizes (C_out must exceed C)");
+    const int G = group_size < N ? group_size : N;
+    SHGAN_CHECK(G >= 1 && G <= 8 && N % G == 0, "batch must be a multiple of the group size (<= 8)");
+    mbstd_append_kernel<<<N / G, 256, 0, (cudaStream_t)stream>>>((const __half*)in_hi, (const __half*)in_lo, (__half*)out_hi,
+                                                               (__half*)out_lo, N, G, H * W, C, C_out);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int shgan_fromrgb(const float* x, const float* w, const float* bias, float wgain, float act_alpha,
                              float act_gain, float act_clamp, void* out_hi, void* out_lo, int N, int Ci, int Co, int H,

@@ -373,3 +373,114 @@ class GeneratorEngine:
         x = x.contiguous().float()
         x_global, feats = self.encoder(x)
         return self.synthesis(x_global, feats, ws, noise_mode=noise_mode, comp_x=x if composite else None)
+
+
+class DiscriminatorEngine:
+    """Discriminator.forward (stylegan.py:828-838) as a launch sequence over the same kernels: per block
+    skip = 1x1 conv(downsample2d(x)) * sqrt(1/2) ; conv0 3x3 ; conv1 = blur + 3x3 stride 2, gain sqrt(1/2), + skip
+    (discrim_block.forward :658-684), then minibatch-std -> conv 3x3 -> fc -> out (discrim_epilogue.forward :743-755)."""
+
+    def __init__(self, D, passes=3, impl=0):
+        self.D, self.passes, self.impl = D, passes, impl
+        self._sig = None
+        self._buf = {}
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.D.parameters()) + list(self.D.buffers()))
+
+    def refresh(self):
+        D = self.D
+        dev = next(D.parameters()).device
+        _check_device(dev)
+        self.dev = dev
+        self.act = _Act(D.activation)
+        self.res_list = list(D.encode_res)
+        f = getattr(D, f'b{self.res_list[0]}').resample_filter
+        self.f_applied = f.detach().to(dev, torch.float32).flip([0, 1]).contiguous()
+        self.blocks = {}
+
+        def conv(l, pad_ci=None):
+            w = l.weight.detach().float()
+            if pad_ci is not None and pad_ci > w.shape[1]:
+                wp = torch.zeros((w.shape[0], pad_ci, w.shape[2], w.shape[3]), dtype=torch.float32, device=dev)
+                wp[:, :w.shape[1]] = w
+                w = wp
+            wh, wl = P.pack_conv_weight(w)
+            return dict(w_hi=wh, w_lo=wl, bias=None if l.bias is None else l.bias.detach(), wgain=float(l.weight_gain),
+                        ci=w.shape[1], co=w.shape[0])
+        for r in self.res_list[:-1]:
+            b = getattr(D, f'b{r}')
+            d = dict(conv0=conv(b.conv0), conv1=conv(b.conv1), skip=conv(b.skip))
+            if b.fromrgb is not None:
+                w = b.fromrgb.weight.detach()
+                d['fromrgb'] = (w.reshape(w.shape[0], w.shape[1]).contiguous(), b.fromrgb.bias.detach(), float(b.fromrgb.weight_gain))
+            self.blocks[r] = d
+        b4 = D.b4
+        c4 = b4.conv.weight.shape[0]
+        self.mbstd = None if b4.mbstd is None else (b4.mbstd.group_size, b4.mbstd.num_channels)
+        if self.mbstd is not None and self.mbstd[1] != 1:
+            raise NotImplementedError('minibatch-std with more than one statistic channel')
+        self.c4 = c4
+        self.c4_pad = (b4.conv.weight.shape[1] + 63) // 64 * 64
+        self.b4 = dict(conv=conv(b4.conv, self.c4_pad),
+                       fc=(b4.fc.weight.detach(), b4.fc.bias.detach(), float(b4.fc.weight_gain), float(b4.fc.bias_gain), _Act(b4.fc.activation_spec)),
+                       out=(b4.out.weight.detach(), b4.out.bias.detach(), float(b4.out.weight_gain), float(b4.out.bias_gain), _Act(b4.out.activation_spec)))
+        self._sig = self._signature()
+
+    def _planes(self, name, n, h, w, c):
+        key = (name, n, h, w, c)
+        if key not in self._buf:
+            self._buf[key] = Planes.empty(n, h, w, c, self.dev)
+        return self._buf[key]
+
+    def _epi(self, L, out, gain=1.0, act=True, skip=None):
+        a = self.act
+        if act and a.on:
+            return K.make_epilogue(wgain=L['wgain'], bias=L['bias'], act=True, act_alpha=a.alpha, act_gain=a.gain * gain,
+                                   act_clamp=a.clamp * gain if a.clamp > 0 else -1.0, skip=skip, out=out)
+        return K.make_epilogue(wgain=L['wgain'], bias=L['bias'], act=False, act_gain=gain, skip=skip, out=out)
+
+    def forward(self, img):
+        if self._sig is None or self._sig != self._signature():
+            self.refresh()
+            self._buf = {}
+        img = img.contiguous().float()
+        n = img.shape[0]
+        g = math.sqrt(0.5)
+        conv = lambda srcs, L, taps, oh, ow, epi: K.conv_igemm(srcs, L['w_hi'], L['w_lo'], taps, oh, ow, epi=epi,
+                                                               passes=self.passes, impl=self.impl)
+        x = None
+        for r in self.res_list[:-1]:
+            d = self.blocks[r]
+            c, cn = d['conv0']['ci'], d['conv1']['co']
+            if 'fromrgb' in d:
+                w, b, wg = d['fromrgb']
+                x = K.fromrgb(img, w, b, wg, self.act.alpha, self.act.gain, self.act.clamp, self._planes(f'd{r}.rgb', n, r, r, c))
+            # skip: downsample2d (blur pad 1, keep even samples) -> 1x1 conv, no bias / activation, gain sqrt(1/2)
+            ds = self._planes(f'd{r}.ds', n, r // 2, r // 2, c)
+            K.fir_nhwc(x, self.f_applied, 1.0, (1, 1, 1, 1), K.make_epilogue(out=ds), parity_split=2)
+            y = self._planes(f'd{r}.skip', n, r // 2, r // 2, cn)
+            conv([ds], d['skip'], P.taps_plain(1, 1), r // 2, r // 2, self._epi(d['skip'], y, gain=g, act=False))
+            # conv0, then conv1 = blur (pad 2) into parity planes + stride-2 conv over them, gain sqrt(1/2), + skip
+            t0 = self._planes(f'd{r}.c0', n, r, r, c)
+            conv([x], d['conv0'], P.taps_plain(3, 3), r, r, self._epi(d['conv0'], t0))
+            ph = (r + 2) // 2
+            par = self._planes(f'd{r}.par', 4 * n, ph, ph, c)
+            K.fir_nhwc(t0, self.f_applied, 1.0, (2, 2, 2, 2), K.make_epilogue(out=par), parity_split=1)
+            srcs = [Planes(par.hi[q * n:(q + 1) * n], par.lo[q * n:(q + 1) * n]) for q in range(4)]
+            x = self._planes(f'd{r}.out', n, r // 2, r // 2, cn)
+            conv(srcs, d['conv1'], P.taps_down2(3), r // 2, r // 2, self._epi(d['conv1'], x, gain=g, skip=y))
+        if self.mbstd is not None:
+            xin = K.mbstd_append(x, self._planes('d4.mb', n, 4, 4, self.c4_pad), self.mbstd[0])
+        else:
+            xin = x
+        t4 = self._planes('d4.conv', n, 4, 4, self.c4)
+        conv([xin], self.b4['conv'], P.taps_plain(3, 3), 4, 4, self._epi(self.b4['conv'], t4))
+        flat = K.planes_to_nchw(t4).view(n, -1)
+        spec = self.b4['fc']
+        h = torch.empty((n, spec[0].shape[0]), dtype=torch.float32, device=self.dev)
+        K.dense(flat, spec[0], spec[1], h, spec[2], spec[3], spec[4].on, spec[4].alpha, spec[4].gain, spec[4].clamp)
+        spec = self.b4['out']
+        out = torch.empty((n, spec[0].shape[0]), dtype=torch.float32, device=self.dev)
+        K.dense(h, spec[0], spec[1], out, spec[2], spec[3], spec[4].on, spec[4].alpha, spec[4].gain, spec[4].clamp)
+        return out

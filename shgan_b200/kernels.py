@@ -172,7 +172,7 @@ def fir_nhwc(src, f, gain, pads, epi, parity_split=False):
         n, ih, iw, c = src.shape
         args = (_p(src), None, None)
     _lib.check(lib.shgan_fir_nhwc(*args, _p(f), f.shape[0], f.shape[1], float(gain), n, c, ih, iw,
-                                 pads[0], pads[1], pads[2], pads[3], C.byref(epi), 1 if parity_split else 0, _stream()),
+                                 pads[0], pads[1], pads[2], pads[3], C.byref(epi), int(parity_split), _stream()),
                'shgan_fir_nhwc')
 
 
@@ -192,6 +192,14 @@ def torgb_combine(img_prev, rgb_partial, bias, f, img_out, comp_x=None, comp_out
     _lib.check(lib.shgan_torgb_combine(_p(img_prev), _p(rgb_partial), rgb_partial.shape[3], _p(bias), _p(f), _p(img_out),
                                       n, h, w, _p(comp_x), _p(comp_out), _stream()), 'shgan_torgb_combine')
     return img_out
+
+
+def mbstd_append(src, out, group_size):
+    n, h, w, c = src.shape
+    lib = _lib.load()
+    _lib.check(lib.shgan_mbstd_append(_p(src.hi), _p(src.lo), _p(out.hi), _p(out.lo), n, h, w, c, out.shape[3], group_size,
+                                     _stream()), 'shgan_mbstd_append')
+    return out
 
 
 # ---- dense / styles ------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@ import torch.nn as nn
 from .. import kernels as K
 from ..engine import GeneratorEngine
 from .common.get_model import get_model, register
+from .stylegan import Discriminator as Discriminator_StyleGan
 from .stylegan import Generator as Generator_StyleGan
 from .stylegan import Mapping as Mapping_StyleGan
 from .stylegan import conv2d_layer, dense, synthesis_layer, torgb_layer
@@ -258,3 +259,9 @@ class Generator(Generator_StyleGan):
         (lib/experiments/shgan_default.py:257-262) -> (img fp32, composite uint8)."""
         img, comp = self.engine().forward(x, z, noise_mode=noise_mode, composite=True)
         return img.clone(), comp
+
+
+@register('comodgan_discriminator', version)
+class Discriminator(Discriminator_StyleGan):
+    """comodgan.py:483-485."""
+    pass

@@ -203,6 +203,102 @@ class Mapping(nn.Module):
         return x
 
 
+class discrim_block(nn.Module):
+    """(fromrgb) -> conv0 -> conv1 (down 2) with an optional 1x1 down-sampling skip branch (stylegan.py:624-684).
+    Parameter container; the arithmetic runs in engine.GeneratorEngine / engine.DiscriminatorEngine."""
+
+    def __init__(self, ic_n, mc_n, oc_n, rgb_n=None, resample_filter=[1, 3, 3, 1],
+                 activation='lrelu_agc(alpha=0.2, gain=sqrt_2, clamp=256)', reslink=False, use_fp16=False):
+        super().__init__()
+        if use_fp16:
+            raise NotImplementedError('fp16 blocks are not used by the released SH-GAN configs')
+        self.register_buffer('resample_filter', P.setup_filter(resample_filter))
+        self.fromrgb = None
+        if rgb_n is not None:
+            self.fromrgb = conv2d_layer(rgb_n, mc_n, 1, bias=True, activation=activation, up=1, down=1, resample_filter=None)
+        self.conv0 = conv2d_layer(ic_n, mc_n, 3, bias=True, activation=activation, up=1, down=1, resample_filter=None)
+        self.conv1 = conv2d_layer(mc_n, oc_n, 3, bias=True, activation=activation, up=1, down=2, resample_filter=resample_filter)
+        self.reslink = reslink
+        if reslink:
+            self.skip = conv2d_layer(mc_n, oc_n, 1, bias=False, activation=None, up=1, down=2, resample_filter=resample_filter)
+        self.use_fp16 = use_fp16
+
+
+class minibatch_std_layer(nn.Module):
+    """stylegan.py:686-705 (parameter-free; runs as shgan_mbstd_append)."""
+
+    def __init__(self, group_size, num_channels=1):
+        super().__init__()
+        self.group_size, self.num_channels = group_size, num_channels
+
+
+class discrim_epilogue(nn.Module):
+    """mbstd -> conv 3x3 -> fc -> out (stylegan.py:707-755)."""
+
+    def __init__(self, ic_n, resolution, cmap_dim, rgb_n=None, mbstd_group_size=4, mbstd_c_n=1,
+                 activation='lrelu_agc(alpha=0.2, gain=sqrt_2, clamp=256)', reslink=True):
+        super().__init__()
+        if rgb_n is not None or cmap_dim is not None:
+            raise NotImplementedError('fromrgb / cmap in the discriminator epilogue are not used by SH-GAN')
+        self.ic_n, self.cmap_dim, self.resolution, self.rgb_n, self.reslink = ic_n, cmap_dim, resolution, rgb_n, reslink
+        self.fromrgb = None
+        self.mbstd = minibatch_std_layer(group_size=mbstd_group_size, num_channels=mbstd_c_n) if mbstd_c_n > 0 else None
+        self.conv = conv2d_layer(ic_n + mbstd_c_n, ic_n, 3, bias=True, activation=activation, up=1, down=1, resample_filter=None)
+        self.fc = dense(ic_n * (resolution ** 2), ic_n, activation=activation)
+        self.out = dense(ic_n, 1, activation=None)
+
+
+@register('stylegan2_discriminator', version)
+class Discriminator(nn.Module):
+    """StyleGAN2 residual discriminator (stylegan.py:757-838); forward(img, c) -> logits [N,1]."""
+
+    def __init__(self, resolution=256, ic_n=3, ch_base=16384, ch_max=512, use_fp16_before_res=16, resample_filter=[1, 3, 3, 1],
+                 activation='lrelu_agc(alpha=0.2, gain=sqrt_2, clamp=256)', mbstd_group_size=4, mbstd_c_n=1, c_dim=None,
+                 cmap_dim=None):
+        super().__init__()
+        log2res = int(np.log2(resolution))
+        if 2 ** log2res != resolution:
+            raise ValueError
+        if use_fp16_before_res is not None:
+            raise NotImplementedError('the released SH-GAN configs run the discriminator in fp32 (use_fp16_before_res: null)')
+        if c_dim is not None and c_dim > 0:
+            raise NotImplementedError('conditional discriminator')
+        self.encode_res = [2 ** i for i in range(log2res, 1, -1)]
+        self.ic_n, self.ch_base, self.ch_max = ic_n, ch_base, ch_max
+        self.resample_filter, self.activation = resample_filter, activation
+        for idx, (ri, rj) in enumerate(zip(self.encode_res[:-1], self.encode_res[1:])):
+            ci, cj = min(ch_base // ri, ch_max), min(ch_base // rj, ch_max)
+            setattr(self, f'b{ri}', discrim_block(ci, ci, cj, rgb_n=ic_n if idx == 0 else None, resample_filter=resample_filter,
+                                                  activation=activation, reslink=True, use_fp16=False))
+        self.mapping = None
+        self.b4 = discrim_epilogue(min(ch_base // self.encode_res[-1], ch_max), resolution=4, cmap_dim=None, activation=activation,
+                                   mbstd_group_size=mbstd_group_size, mbstd_c_n=mbstd_c_n)
+        self.__dict__['_engine_obj'] = None
+
+    def engine(self, passes=None, impl=None):
+        from ..engine import DiscriminatorEngine
+        eng = self.__dict__.get('_engine_obj')
+        if eng is None:
+            eng = DiscriminatorEngine(self)
+            self.__dict__['_engine_obj'] = eng
+        if passes is not None:
+            eng.passes = passes
+        if impl is not None:
+            eng.impl = impl
+        return eng
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == '_engine_obj' else copy.deepcopy(v, memo)
+        return new
+
+    def forward(self, img, c=None, **kwargs):
+        return self.engine().forward(img)
+
+
 @register('stylegan2_generator', version)
 class Generator(nn.Module):
     """mapping + synthesis container (stylegan.py:582-606); sub-configs or ready modules are accepted."""

@@ -65,7 +65,10 @@ def _apply_epi(acc, e, block_n, parity_split=False):
         if e['next_scale'] is not None:
             v = v * e['next_scale'][:, None, None, :]
         hi, lo = _split(v)
-        if parity_split:
+        if parity_split == 2:
+            e['out'].hi.copy_(hi[:, ::2, ::2])
+            e['out'].lo.copy_(lo[:, ::2, ::2])
+        elif parity_split:
             ph, pw = (oh + 1) // 2, (ow + 1) // 2
             oh_, ol_ = e['out'].hi.view(4, n, ph, pw, co), e['out'].lo.view(4, n, ph, pw, co)
             for py in range(2):
@@ -182,6 +185,18 @@ def torgb_combine(img_prev, rgb_partial, bias, f, img_out, comp_x=None, comp_out
     return img_out
 
 
+def mbstd_append(src, out, group_size):
+    from oracle import shgan_oracle as O
+    x = src.float().permute(0, 3, 1, 2).numpy()
+    y = torch.from_numpy(O.minibatch_std(x, group_size, 1)).permute(0, 2, 3, 1)
+    full = torch.zeros(out.shape, dtype=torch.float32)
+    full[..., :y.shape[3]] = y
+    hi, lo = _split(full)
+    out.hi.copy_(hi)
+    out.lo.copy_(lo)
+    return out
+
+
 def dense(x0, w, bias, out, wgain, bgain=1.0, act=False, act_alpha=0.2, act_gain=math.sqrt(2.0), act_clamp=256.0, x1=None):
     x = x0 if x1 is None else torch.cat([x0, x1], dim=1)
     v = (x @ w.T) * wgain
@@ -234,7 +249,7 @@ def install(monkeypatch):
     """Patch shgan_b200.kernels (and the engine's device check) with the CPU emulation."""
     import shgan_b200.engine as E
     for name in ['make_epilogue', 'conv_num_nblocks', 'conv_igemm', 'fir_nhwc', 'nchw_to_planes', 'planes_to_nchw',
-                 'planes_add_nchw', 'nhwc_to_nchw_f32', 'fromrgb', 'torgb_combine', 'dense', 'normalize_2nd_moment',
+                 'planes_add_nchw', 'nhwc_to_nchw_f32', 'fromrgb', 'torgb_combine', 'mbstd_append', 'dense', 'normalize_2nd_moment',
                  'style_prep', 'shu_workspace_bytes', 'shu_fwd']:
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(E, '_check_device', lambda dev: None)

@@ -289,6 +289,34 @@ def gen_generator(R, only=None):
         save(name, **out)
 
 
+DISCRIMINATOR_CASES = [
+    # name, resolution, ch_base, ch_max, batch, seed
+    ('disc128_c64', 128, 8192, 64, 4, 21),
+    ('disc256', 256, 32768, 512, 8, 22),
+]
+
+
+def gen_discriminator(R):
+    for name, res, chb, chm, batch, seed in DISCRIMINATOR_CASES:
+        sd = O.synthetic_discriminator_state_dict(res, seed=seed, ch_base=chb, ch_max=chm)
+        D = R.comodgan.Discriminator(resolution=res, ic_n=4, ch_base=chb, ch_max=chm, use_fp16_before_res=None).eval().requires_grad_(False)
+        D.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+        assert list(D.state_dict().keys()) == [k for k, _ in O.discriminator_state_dict_spec(res, ch_base=chb, ch_max=chm)]
+        x, _ = O.synthetic_inputs(batch, res, seed=seed)
+        inter = {}
+        hooks = []
+        for r in (8, 16):
+            blk = getattr(D, f'b{r}')
+            hooks.append(blk.register_forward_hook(lambda m, i, o, r=r: inter.__setitem__(r // 2, o[0].numpy().copy())))
+        with torch.no_grad():
+            y = D(t(x), None).numpy()
+        for h in hooks:
+            h.remove()
+        yo, io = O.discriminator(sd, x, res, return_intermediates=True)
+        print(f'  {name}: out {y.ravel()[:4]}  oracle err {err(y, yo):.2e}  x4 err {err(inter[4], io[4]):.2e}')
+        save(name, out=y, x4=inter[4], x8=inter[8])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', default=None)
@@ -301,6 +329,9 @@ def main():
         if args.only in (None, nm):
             print(nm)
             fn(R)
+    if args.only in (None, 'discriminator'):
+        print('discriminator')
+        gen_discriminator(R)
     if args.only is None or args.only.startswith('gen'):
         print('generator')
         gen_generator(R, None if args.only in (None, 'generator') else args.only)

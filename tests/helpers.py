@@ -30,3 +30,12 @@ def build_generator(res, sd, ch_base=32768, ch_max=512, device='cpu'):
         pass
     G.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
     return G.eval().requires_grad_(False).to(device)
+
+
+def build_discriminator(res, sd, ch_base=32768, ch_max=512, device='cpu'):
+    """`comodgan_discriminator` with the args of configs/model/comodgan.yaml:51-58."""
+    from shgan_b200.model_zoo import get_model
+    D = get_model()(dict(type='comodgan_discriminator', args=dict(ic_n=4, ch_base=ch_base, ch_max=ch_max, resolution=res,
+                                                                  use_fp16_before_res=None)))
+    D.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    return D.eval().requires_grad_(False).to(device)

@@ -11,7 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle import shgan_oracle as O  # noqa: E402  (checker only)
-from golden.make_golden import CONV_CASES, MODCONV_CASES, modconv_inputs, rng, GENERATOR_CASES  # noqa: E402
+from golden.make_golden import CONV_CASES, MODCONV_CASES, modconv_inputs, rng, GENERATOR_CASES, DISCRIMINATOR_CASES  # noqa: E402
 import helpers as H  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -192,3 +192,35 @@ def test_generator_tc_state_dict_reload_and_deepcopy():
     assert np.array_equal(G2(t(x), t(z), None, noise_mode='const').cpu().numpy(), a)
     ref = O.generator(sd2, x, z, 128)
     assert np.abs(b - ref).max() <= 1e-3
+
+
+# ------------------------------------------------------------------------------- discriminator
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('case', DISCRIMINATOR_CASES, ids=[c[0] for c in DISCRIMINATOR_CASES])
+def test_discriminator_golden(case, impl, golden):
+    name, res, chb, chm, batch, seed = case
+    D = H.build_discriminator(res, O.synthetic_discriminator_state_dict(res, seed=seed, ch_base=chb, ch_max=chm), chb, chm, device=DEV)
+    D.engine(impl=impl)
+    x, _ = O.synthetic_inputs(batch, res, seed=seed)
+    y = D(t(x), None).cpu().numpy()
+    ref = golden(name)['out']
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()), np.abs(y - ref).max()
+
+
+def test_generator_then_discriminator_tc_step():
+    """C4-style step: G forward -> composite -> D(cat[mask - 0.5, fake]) on the tensor-core path vs the oracle."""
+    sd_g = O.synthetic_state_dict(128, seed=5, ch_base=8192, ch_max=64)
+    sd_d = O.synthetic_discriminator_state_dict(128, seed=5, ch_base=8192, ch_max=64)
+    G = H.build_generator(128, sd_g, 8192, 64, device=DEV)
+    D = H.build_discriminator(128, sd_d, 8192, 64, device=DEV)
+    x, z = O.synthetic_inputs(4, 128, seed=5)
+    img = G(t(x), t(z), None, noise_mode='const')
+    m = t(x)[:, 0:1] + 0.5
+    fake = t(x)[:, 1:4] * m + img * (1 - m)
+    logits = D(torch.cat([t(x)[:, 0:1], fake], dim=1), None).cpu().numpy()
+    img_ref = O.generator(sd_g, x, z, 128)
+    mr = x[:, 0:1] + 0.5
+    fake_ref = x[:, 1:4] * mr + img_ref * (1 - mr)
+    ref = O.discriminator(sd_d, np.concatenate([x[:, 0:1], fake_ref], axis=1).astype(np.float32), 128)
+    assert np.abs(logits - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())

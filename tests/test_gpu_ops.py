@@ -228,3 +228,23 @@ def test_shu_golden(golden):
     ref = O.shu_forward(sd, xb)
     for r in ref:
         assert relerr(yb[r].cpu().numpy(), ref[r]) <= 2e-5
+
+
+def test_fir_decimate_and_mbstd():
+    from shgan_b200 import kernels as K
+    r = np.random.default_rng(8)
+    f = O.setup_filter([1, 3, 3, 1])
+    x = r.standard_normal((3, 32, 12, 10)).astype(np.float32)
+    xp = K.nchw_to_planes(t(x))
+    out = K.Planes.empty(3, 6, 5, 32, DEV)
+    ft = t(f)
+    K.fir_nhwc(xp, ft, 1.0, (1, 1, 1, 1), K.make_epilogue(out=out), parity_split=2)
+    ref = O.upfirdn2d(x, f, down=2, padding=[1, 1, 1, 1])
+    assert relerr(K.planes_to_nchw(out).cpu().numpy(), ref) <= 3e-6
+    # minibatch std (group 4, 1 channel) fused with the concat and channel padding
+    xb = r.standard_normal((8, 64, 4, 4)).astype(np.float32)
+    pb = K.nchw_to_planes(t(xb))
+    ob = K.mbstd_append(pb, K.Planes.empty(8, 4, 4, 128, DEV), 4)
+    got = K.planes_to_nchw(ob).cpu().numpy()
+    refb = O.minibatch_std(xb, 4, 1)
+    assert relerr(got[:, :65], refb) <= 3e-6 and np.abs(got[:, 65:]).max() == 0

@@ -12,7 +12,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle import shgan_oracle as O  # noqa: E402
-from golden.make_golden import CONV_CASES, MODCONV_CASES, modconv_inputs, rng  # noqa: E402
+from golden.make_golden import CONV_CASES, MODCONV_CASES, DISCRIMINATOR_CASES, modconv_inputs, rng  # noqa: E402
 import fake_backend as FB  # noqa: E402
 import helpers as H  # noqa: E402
 
@@ -138,6 +138,16 @@ def test_engine_generator_matches_golden(fake, golden):
     assert np.abs(G(t(x), t(z), None, noise_mode='none').numpy() - O.generator(sd, x, z, res, noise_mode='none')).max() <= 1e-3
 
 
+@pytest.mark.parametrize('case', DISCRIMINATOR_CASES, ids=[c[0] for c in DISCRIMINATOR_CASES])
+def test_engine_discriminator_matches_golden(case, fake, golden):
+    name, res, chb, chm, batch, seed = case
+    D = H.build_discriminator(res, O.synthetic_discriminator_state_dict(res, seed=seed, ch_base=chb, ch_max=chm), chb, chm)
+    assert list(D.state_dict().keys()) == [k for k, _ in O.discriminator_state_dict_spec(res, ch_base=chb, ch_max=chm)]
+    x, _ = O.synthetic_inputs(batch, res, seed=seed)
+    y = D(t(x), None).numpy()
+    assert y.shape == (batch, 1) and np.abs(y - golden(name)['out']).max() <= 1e-5
+
+
 def test_state_dict_contract_and_registry():
     from shgan_b200.model_zoo import get_model
     for res in (256, 512):
@@ -153,7 +163,7 @@ def test_state_dict_contract_and_registry():
     with pytest.raises(RuntimeError):
         G.load_state_dict({'mapping.w_avg': torch.zeros(512)}, strict=True)
     with pytest.raises(KeyError):
-        get_model()(dict(type='comodgan_discriminator', args={}))
+        get_model()(dict(type='resnet50', args={}))
     G2 = copy.deepcopy(G)
     assert G2.encoder._owner() is G2 and G.encoder._owner() is G
 
