@@ -120,9 +120,11 @@ typedef struct {
     shgan_epilogue epi;
     int block_n;                 /* GEMM tile width: 0 = auto (widest of 64/128/256 that still fills the SMs) */
     int passes;                  /* 3 = fp32-class (default when 0), 1 = hi*hi only (fast, ~fp16 accuracy) */
-    int impl;                    /* 0 = tcgen05 tensor-core kernel (the product path);
+    int impl;                    /* 0 = tcgen05 tensor-core path (the product): the halo-tile kernel for the large layers,
+                                        the per-tap kernel for the small ones, chosen per layer;
                                     1 = fp32 FMA kernel with identical operands/epilogue, kept ONLY as the on-device
-                                        cross-check of the tensor-core kernel at full layer sizes (tests) */
+                                        cross-check of the tensor-core kernels at full layer sizes (tests);
+                                    2 / 3 = force the per-tap / the halo-tile tensor-core kernel (tests, profiling) */
 } shgan_conv_desc;
 int shgan_conv_igemm(const shgan_conv_desc* d, void* stream);
 /* size of the rgb partial axis: Co / 32 (independent of block_n, kept in the signature for ABI stability) */

@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('SHGAN_NVCC_FLAGS', '').split()
 
 
 def _sources():

@@ -41,6 +41,8 @@ extern "C" int shgan_conv_igemm(const shgan_conv_desc* d, void* stream_) {
     const ConvGeom g = make_geom(*d);
     const EpiParams epi = d->mode == 0 ? make_epi(d->epi) : EpiParams{};
     if (d->impl == 1) return launch_conv_simt(g, epi, bn, stream);
-    SHGAN_CHECK(d->impl == 0, "impl must be 0 or 1");
-    return launch_conv_tc(g, epi, bn, d->passes == 0 ? 3 : d->passes, stream);
+    SHGAN_CHECK(d->impl == 0 || d->impl == 2 || d->impl == 3, "impl must be 0, 1, 2 or 3");
+    const int passes = d->passes == 0 ? 3 : d->passes;
+    if (d->impl == 3 || (d->impl == 0 && bn == 0 && conv_prefers_halo(g))) return launch_conv_halo(g, epi, bn, passes, stream);
+    return launch_conv_tc(g, epi, bn, passes, stream);
 }

@@ -40,6 +40,9 @@ static inline ConvGeom make_geom(const shgan_conv_desc& d) {
 
 int launch_conv_simt(const ConvGeom& g, const EpiParams& epi, int block_n, cudaStream_t stream);
 int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream);
+int launch_conv_halo(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream);
+double conv_halo_efficiency(const ConvGeom& g);
+bool conv_prefers_halo(const ConvGeom& g);
 
 // torgb partial sums are produced per block of 32 output channels, independent of the GEMM tile width
 constexpr int CONV_RGB_BLOCK = 32;
@@ -49,7 +52,88 @@ static inline int conv_block_n(int Co, int block_n) {
     return block_n;
 }
 
+// vectors staged per tile by the tensor-core kernels: dcoef*wgain, bias, next_scale, rgb_w[0..2]*rgb_style
+constexpr int CONV_STG_VECS = 6;
+
 #ifdef __CUDACC__
+// The per-(sample, channel) vectors of the fused epilogue (semantics: `shgan_epilogue` in include/shgan_b200.h) are
+// staged in shared memory once per tile: the tile's final epilogue then runs on LDS broadcasts instead of ~20 dependent
+// L2 round trips per 16 channels.  That matters because the epilogue warps also drain the TMEM accumulation chunks: while
+// they are in a tile's final epilogue the MMA issuer can only run two chunks ahead.
+//   stg[0][i] = (dcoef ? dcoef[n,o] : 1) * wgain     stg[1][i] = bias ? bias[o] : 0     stg[2][i] = next_scale ? .. : 1
+//   stg[3+j][i] = rgb_w[j,o] * rgb_style[n,o]        (o = o_base + i)
+template <int BN, int NTHREADS>
+__device__ __forceinline__ void stage_epilogue_vectors(const EpiParams& p, float* stg, int n, int Co, int o_base, int et) {
+    for (int i = et; i < BN; i += NTHREADS) {
+        const int o = o_base + i;
+        const long long no = (long long)n * Co + o;
+        stg[i] = (p.dcoef ? __ldg(p.dcoef + no) : 1.f) * p.wgain;
+        stg[BN + i] = p.bias ? __ldg(p.bias + o) : 0.f;
+        stg[2 * BN + i] = p.next_scale ? __ldg(p.next_scale + no) : 1.f;
+        if (p.rgb_w) {
+            const float st = __ldg(p.rgb_style + no);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) stg[(3 + j) * BN + i] = __ldg(p.rgb_w + (long long)j * Co + o) * st;
+        }
+    }
+}
+
+// fused epilogue on CH consecutive channels (tile-local index oi, global index o0) of output pixel (n,y,x); nz = the
+// pixel's noise value already multiplied by the noise strength (0 when the layer has no noise)
+template <int BN, int CH>
+__device__ __forceinline__ void epilogue_apply_staged(const EpiParams& p, const float* stg, float* v, float nz, int Co, int o0, int oi,
+                                                      float* rgb, long long pix) {
+#pragma unroll
+    for (int i = 0; i < CH; i += 4) {
+        const float4 d = *reinterpret_cast<const float4*>(stg + oi + i);
+        const float4 b = *reinterpret_cast<const float4*>(stg + BN + oi + i);
+        v[i] = v[i] * d.x + nz + b.x; v[i + 1] = v[i + 1] * d.y + nz + b.y;
+        v[i + 2] = v[i + 2] * d.z + nz + b.z; v[i + 3] = v[i + 3] * d.w + nz + b.w;
+    }
+    if (p.act) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = lrelu_agc(v[i], p.act_alpha, p.act_gain, p.act_clamp);
+    } else if (p.act_gain != 1.f) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] *= p.act_gain;
+    }
+    if (p.skip_hi) {
+#pragma unroll
+        for (int i = 0; i < CH; i += 8) {
+            float s[8];
+            load_planes8(p.skip_hi, p.skip_lo, pix * Co + o0 + i, s);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i + j] += s[j];
+        }
+    }
+    if (p.rgb_w) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) {
+                const float4 w = *reinterpret_cast<const float4*>(stg + (3 + j) * BN + oi + i);
+                rgb[j] = fmaf(v[i], w.x, rgb[j]); rgb[j] = fmaf(v[i + 1], w.y, rgb[j]);
+                rgb[j] = fmaf(v[i + 2], w.z, rgb[j]); rgb[j] = fmaf(v[i + 3], w.w, rgb[j]);
+            }
+        }
+    }
+    if (p.out_f32) {
+#pragma unroll
+        for (int i = 0; i < CH; i += 4)
+            *reinterpret_cast<float4*>(p.out_f32 + pix * Co + o0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    if (p.out_hi) {
+#pragma unroll
+        for (int i = 0; i < CH; i += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(stg + 2 * BN + oi + i);
+            v[i] *= sc.x; v[i + 1] *= sc.y; v[i + 2] *= sc.z; v[i + 3] *= sc.w;
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i += 8) store_planes8(p.out_hi, p.out_lo, pix * Co + o0 + i, v + i);
+    }
+}
+
+
 // raw-mode store of CH consecutive channels of output pixel (n,y,x) into the strided z tensor
 template <int CH>
 __device__ __forceinline__ void raw_store(const ConvGeom& g, const float* v, int n, int y, int x, int o0) {

@@ -25,7 +25,7 @@
 //   epilogue warps drain the other one and add it into fp32 registers with round-to-nearest FADDs.  This
 //   bounds the truncation chain for every layer width and is also what overlaps epilogue and MMA.
 #include "conv_common.cuh"
-#include "tma_util.cuh"
+#include "tc_ptx.cuh"
 
 namespace shgan {
 
@@ -53,78 +53,17 @@ constexpr int TC_M = 128;       // output pixels per tile == UMMA M
 constexpr int TC_MAX_CHUNK_ITERS = 4;   // (tap, slab) steps chained in one TMEM accumulator = 48 MMAs
 constexpr int TC_KC = 64;       // channels per K slab (= 128 B of fp16 = one swizzle row)
 constexpr int A_BYTES = TC_M * TC_KC * 2;
+constexpr int TC_STG_VECS = CONV_STG_VECS;
 
 template <int BN> struct TcCfg {
     static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
     static constexpr int B_BYTES = BN * TC_KC * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = 2 * BN;   // power of two >= 32
+    static constexpr int STG_BYTES = TC_STG_VECS * BN * 4;   // per-tile epilogue vectors (stage_epilogue_vectors)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
+    static constexpr int TMEM_COLS = 512;      // the whole tensor memory (one CTA per SM)
+    static constexpr int NACC = TMEM_COLS / BN;   // accumulator buffers: the MMA issuer may run NACC chunks ahead of the epilogue
 };
-
-// ---- PTX wrappers (mbarrier / TMA wrappers live in tma_util.cuh) ------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start address >> 4 in [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major, set to 1),
-// SBO >> 4 in [32,46) = 1024 B between 8-row groups, version 1 in [46,48), layout type 2 in [61,64).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, issued by one thread for the CTA
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives on `bar` once every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 32 lanes x 16 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // ---- kernel -------------------------------------------------------------------------------------
 template <int BN>
@@ -138,9 +77,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* full_bar = bars;                    // [STAGES] TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;          // [STAGES] MMA -> TMA
-    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2] MMA -> epilogue
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2] epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    constexpr int NACC = Cfg::NACC;
+    uint64_t* tfull_bar = bars + 2 * STAGES;             // [NACC] MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * STAGES + NACC;     // [NACC] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NACC);
+    float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [TC_STG_VECS][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kslabs = g.C / TC_KC;
@@ -157,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NACC; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], TC_EPI_THREADS);
         }
@@ -178,7 +119,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_DEC));
       if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = (passes == 3 ? 2u : 1u) * (uint32_t)(A_BYTES + Cfg::B_BYTES);
@@ -210,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A/B fp16 (0), both K-major,
             // N>>3 in [17,23), M>>4 in [24,29)
             constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
@@ -243,8 +184,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(&tfull_bar[acc]);        // chunk accumulator complete -> epilogue warps
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1;
+                    if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                 }
             }
         }
@@ -272,6 +212,17 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
             const bool valid = n < g.N && y < g.OH && x < g.OW;
             const long long pix = ((long long)n * g.OH + y) * g.OW + x;
 
+            // one image per tile (every layer from 16x16 up): stage the per-(sample, channel) epilogue vectors in shared
+            // memory and fetch the pixel's noise now, so that the tile's final epilogue needs no dependent L2 round trips
+            const bool staged = ti.TN == 1 && g.mode == 0;
+            float nz = 0.f;
+            if (staged) {
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+                stage_epilogue_vectors<BN, TC_EPI_THREADS>(epi, stg, n, g.Co, nb * BN, (int)threadIdx.x - (TC_THREADS - TC_EPI_THREADS));
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+                if (epi.noise && valid) nz = __ldg(epi.noise + (long long)n * epi.noise_sn + (long long)y * g.OW + x) * __ldg(epi.noise_strength);
+            }
+
             float accv[HN];
             for (int c = 0; c < nchunks; ++c) {
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -286,15 +237,16 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
             if (valid) {
                 float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                 for (int p = 0; p < HN / 16; ++p) {
-                    const int o0 = nb * BN + half * HN + p * 16;
+                    const int oi = half * HN + p * 16;
+                    const int o0 = nb * BN + oi;
                     if (g.mode == 1) raw_store<16>(g, accv + p * 16, n, y, x, o0);
+                    else if (staged) epilogue_apply_staged<BN, 16>(epi, stg, accv + p * 16, nz, g.Co, o0, oi, rgb, pix);
                     else epilogue_apply<16>(epi, accv + p * 16, n, y, x, g.OH, g.OW, g.Co, o0, rgb, pix);
                     if ((p & 1) && g.mode == 0 && epi.rgb_w) {   // one torgb partial per CONV_RGB_BLOCK = 32 channels
                         float* dst = epi.rgb_out + (pix * (g.Co / CONV_RGB_BLOCK) + (o0 - 16) / CONV_RGB_BLOCK) * 4;

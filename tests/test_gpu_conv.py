@@ -1,5 +1,6 @@
 """GPU parity tests of the convolution hot path (`-m gpu`).  Test names carry `simt` (fp32 FMA cross-check
-kernel, desc.impl=1) or `tc` (tcgen05 tensor-core kernel, the product path) so the two can be run in separate
+kernel, desc.impl=1) or `tc` (tcgen05 tensor-core kernels, the product path: `tc` = per-layer choice as shipped,
+`tc_tap` / `tc_halo` = the per-tap / the halo-tile kernel forced for every layer) so the two can be run in separate
 processes: `pytest -m gpu -k "not tc"` then `pytest -m gpu -k tc`.
 """
 import os
@@ -16,7 +17,7 @@ import helpers as H  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
-IMPLS = [pytest.param(1, id='simt'), pytest.param(0, id='tc')]
+IMPLS = [pytest.param(1, id='simt'), pytest.param(0, id='tc'), pytest.param(2, id='tc_tap'), pytest.param(3, id='tc_halo')]
 
 
 def t(a):
@@ -49,6 +50,9 @@ SHAPES = [
     (3, 64, 256, 8, 8),      # TN = 2, BN = 256
     (1, 192, 64, 5, 7),      # odd sizes -> pow2 tile larger than the image
     (2, 64, 512, 9, 33),     # 2 N blocks of 256
+    (1, 64, 64, 70, 45),     # halo kernel: several tiles in x and y with ragged edges
+    (2, 128, 128, 33, 64),   # halo kernel: BN = 128, 2 K slabs
+    (1, 256, 192, 40, 40),   # 4 K slabs (chunked accumulation across slabs), Co = 3 x 64
 ]
 
 
@@ -73,6 +77,10 @@ def test_igemm_tc_single_pass_and_block_n():
     assert 1e-5 < relerr(y1, ref) <= 3e-3      # fp16-rounded operands: visibly worse than the split path, still sane
     for bn in (64, 128, 256):
         assert relerr(_igemm_plain(x, wt, 0, block_n=bn), ref) <= 3e-6
+    y1 = _igemm_plain(x, wt, 3, passes=1)
+    assert 1e-5 < relerr(y1, ref) <= 3e-3
+    for bn in (64, 128):
+        assert relerr(_igemm_plain(x, wt, 3, block_n=bn), ref) <= 3e-6
 
 
 @pytest.mark.parametrize('impl', IMPLS)
@@ -147,8 +155,20 @@ def test_generator_tc_gen128(golden):
     _check_generator('gen128_c64', 0, golden, 1e-3)
 
 
+def test_generator_tc_halo_gen128(golden):
+    _check_generator('gen128_c64', 3, golden, 1e-3)    # every layer (4x4 .. 128x128, down-2, up-2 passes) on the halo kernel
+
+
+def test_generator_tc_tap_gen128(golden):
+    _check_generator('gen128_c64', 2, golden, 1e-3)
+
+
 def test_generator_tc_gen256(golden):
     _check_generator('gen256', 0, golden, 1e-3)        # north_star: within 1e-3 max-abs of the reference
+
+
+def test_generator_tc_halo_gen256(golden):
+    _check_generator('gen256', 3, golden, 1e-3)
 
 
 def test_generator_tc_gen512(golden):
@@ -162,12 +182,12 @@ def test_generator_tc_vs_simt_batch_and_random_noise():
     G = H.build_generator(256, sd, device=DEV)
     x, z = O.synthetic_inputs(3, 256, seed=3)
     outs = {}
-    for impl in (1, 0):
+    for impl in (1, 0, 3):
         G.engine(impl=impl)
         torch.manual_seed(123)
         outs[impl] = G(t(x), t(z), None, noise_mode='random').cpu().numpy()
-    scale = np.abs(outs[1]).max()
     assert np.abs(outs[0] - outs[1]).max() <= 1e-3, np.abs(outs[0] - outs[1]).max()
+    assert np.abs(outs[3] - outs[1]).max() <= 1e-3, np.abs(outs[3] - outs[1]).max()
     G.engine(impl=0)
     torch.manual_seed(123)
     again = G(t(x), t(z), None, noise_mode='random').cpu().numpy()

@@ -1,0 +1,206 @@
+// Hardware probe (development aid, not product code): issue rate of tcgen05.mma kind::f16 M=128 with both operands in
+// shared memory (SWIZZLE_128B, K-major), as a function of N and of the A start-address row shift used by the halo-tile
+// convolution.  No global traffic: operands are whatever shared memory holds.  Reports clocks per MMA (K=16).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I shgan_b200/csrc -I include tools/mma_rate_probe.cu -o build/mma_rate_probe
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "tma_util.cuh"
+
+using namespace shgan;
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// mode 0: every MMA reads the same A/B (k advances inside one 64-wide slab); mode 1: conv-like sequence: per "step" and
+// M-block the 4 k-slices x {A_hi*W, A_lo*W} then A_hi*W_lo, A views shifted by `shift` rows, 2 M-blocks, 2 accumulators.
+template <int N>
+__global__ void probe(long long* out, int iters, int shift, int mode, int contend, const uint8_t* gsrc, float* gsink, int commit_every) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sa_hi = smem_u32(smem);                  // 400 rows x 128 B = 51200
+    const uint32_t sa_lo = sa_hi + 51200;
+    const uint32_t sb_hi = sa_lo + 51200;                   // 256 x 128 B
+    const uint32_t sb_lo = sb_hi + 32768;
+    uint8_t* scratch = smem + 2 * 51200 + 2 * 32768;   // 32 KB landing zone for the contention copies
+    uint64_t* bar = (uint64_t*)(scratch + 32768);
+    uint32_t* slot = (uint32_t*)(bar + 8);
+    volatile int* stop = (volatile int*)(bar + 7);
+    const int warp = threadIdx.x >> 5;
+    // zero the operands (denormals / NaNs could change data-dependent power, not timing; keep it clean)
+    for (int i = threadIdx.x; i < (2 * 51200 + 2 * 32768) / 4; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + 12345u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        // contend bit 4: random fp16 operands in (-2, 2) (sign + 10 mantissa bits random, exponent 0x3c00/0x3800 region), else all 1.0
+        ((uint32_t*)smem)[i] = (contend & 16) ? ((h & 0x87ff87ffu) | 0x38003800u) : 0x3c003c00u;
+    }
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); for (int i = 1; i < 5; ++i) mbar_init(&bar[i], 1); mbar_init(&bar[5], 1); mbar_init(&bar[6], 1); mbar_arrive(&bar[6]); *stop = 0; mbar_fence_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    if (warp == 0 && elect_one()) {
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        long long n_mma = 0;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (mode == 0) {
+                for (int k = 0; k < 4; ++k) {
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                 ::"r"(tmem), "l"(desc_sw128(sa_hi + shift * 128 + k * 32)), "l"(desc_sw128(sb_hi + k * 32)), "r"(idesc), "r"(1u) : "memory");
+                }
+                n_mma += 4;
+            } else {
+                const uint32_t toff = (uint32_t)((shift * (it & 3) + (it & 7)) * 128);
+                if (commit_every >= 10) { mbar_wait(&bar[6], 0); if (commit_every != 12) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                for (int blk = 0; blk < 2; ++blk)
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t ao = toff + blk * 16384 + k * 32;
+                        const uint64_t db = desc_sw128(sb_hi + k * 32);
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(tmem + blk * N), "l"(desc_sw128(sa_hi + ao)), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(tmem + blk * N), "l"(desc_sw128(sa_lo + ao)), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                    }
+                if (commit_every >= 10 && commit_every != 13) { mbar_wait(&bar[6], 0); if (commit_every != 12) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                if (commit_every == 1 || commit_every == 2 || commit_every == 11)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[5])) : "memory");
+                for (int blk = 0; blk < 2; ++blk)
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t ao = toff + blk * 16384 + k * 32;
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(tmem + blk * N), "l"(desc_sw128(sa_hi + ao)), "l"(desc_sw128(sb_lo + k * 32)), "r"(idesc), "r"(1u) : "memory");
+                    }
+                if (commit_every == 1 || commit_every == 11)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[5])) : "memory");
+                n_mma += 24;
+            }
+            if (commit_every == 3 || (commit_every == 6 && (it & 1)))
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[5])) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[0])) : "memory");
+        mbar_wait(&bar[0], 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = n_mma; }
+        *stop = 1;
+    } else if (warp >= 4 && (contend & 64)) {
+        // 8 warps polling an mbarrier that never completes (what epilogue warps waiting for the MMA do)
+        long long n = 0;
+        while (!*stop && n < 2000000) { mbar_try_wait(&bar[6], 1); ++n; }
+        if (blockIdx.x == 0 && threadIdx.x == 128) out[3] = n;
+        if (n == 123456789) gsink[3] = (float)n;
+    } else if (warp >= 4 && (contend & 128)) {
+        // same, but one polling lane per warp and a nanosleep back-off
+        long long n = 0;
+        while (!*stop && n < 2000000) { if ((threadIdx.x & 31) == 0) { mbar_try_wait(&bar[6], 1); __nanosleep(100); } ++n; __syncwarp(); }
+        if (blockIdx.x == 0 && threadIdx.x == 128) out[3] = n;
+        if (n == 123456789) gsink[3] = (float)n;
+    } else if (warp >= 4 && warp < 8 && (contend & 1)) {
+        // tcgen05.ld of the accumulator columns the MMAs do not write (256..511), 32 columns at a time
+        float acc = 0.f;
+        while (!*stop) {
+            for (int c = 256; c < 512; c += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + c;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int i = 0; i < 32; ++i) acc += __uint_as_float(r[i]);
+            }
+        }
+        if (acc == 123.456f) gsink[0] = acc;
+    } else if (warp == 1 && (contend & 2)) {
+        // bulk copies global -> shared (the TMA write path), 4 x 8 KB in flight
+        if (threadIdx.x == 32) {
+            uint32_t ph[4] = {0, 0, 0, 0};
+            long long n = 0;
+            for (int i = 0; i < 4; ++i) {
+                mbar_expect_tx(&bar[1 + i], 8192);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(scratch + i * 8192)), "l"(gsrc + ((blockIdx.x * 4 + i) * 8192)), "r"(8192), "r"(smem_u32(&bar[1 + i])) : "memory");
+            }
+            while (!*stop) {
+                for (int i = 0; i < 4; ++i) {
+                    mbar_wait(&bar[1 + i], ph[i]);
+                    ph[i] ^= 1;
+                    ++n;
+                    mbar_expect_tx(&bar[1 + i], 8192);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(scratch + i * 8192)), "l"(gsrc + ((blockIdx.x * 4 + i) * 8192)), "r"(8192), "r"(smem_u32(&bar[1 + i])) : "memory");
+                }
+            }
+            for (int i = 0; i < 4; ++i) mbar_wait(&bar[1 + i], ph[i]);
+            if (blockIdx.x == 0) out[2] = n * 8192;
+        }
+    } else if (warp >= 8 && (contend & 4)) {
+        // plain shared-memory loads (LDS.128), conflict-free
+        float acc = 0.f;
+        const float4* p = (const float4*)scratch;
+        while (!*stop) {
+            for (int i = 0; i < 16; ++i) { float4 v = p[(threadIdx.x & 127) + 128 * i]; acc += v.x + v.y + v.z + v.w; }
+        }
+        if (acc == 123.456f) gsink[1] = acc;
+    } else if (warp >= 8 && (contend & 8)) {
+        // L1 traffic like register spills / epilogue stores: per-thread global store + load of 16 B
+        float4* g = (float4*)(gsink + 1024) + (size_t)blockIdx.x * 4096 + threadIdx.x;
+        float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+        while (!*stop) {
+            for (int i = 0; i < 8; ++i) { g[i * 512] = v; }
+            for (int i = 0; i < 8; ++i) { float4 w = g[i * 512]; v.x += w.y; }
+        }
+        if (v.x == 123.456f) gsink[2] = v.x;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+static uint8_t* g_src; static float* g_sink;
+template <int N>
+void run(long long* dout, int grid, int shift, int mode, int contend = 0, int commit_every = 0) {
+    const int smem_bytes = 1024 + 2 * 51200 + 2 * 32768 + 32768 + 128;
+    cudaFuncSetAttribute(probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    const int iters = mode == 0 ? 4000 : ((contend & 32) ? 40000 : 200);
+    cudaMemset(dout, 0, 32);
+    probe<N><<<grid, 384, smem_bytes>>>(dout, iters, shift, mode, contend, g_src, g_sink, commit_every);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
+    long long h[4];
+    cudaMemcpy(h, dout, 32, cudaMemcpyDeviceToHost);
+    const double cpm = (double)h[0] / (double)h[1];
+    printf("N=%3d grid=%3d mode=%d shift=%2d contend=%2d commit_every=%d: %7.1f clk/MMA  (floor %d)  -> %.0f%% of the tensor floor; bulk-copy %.1f B/clk; polls/warp %lld\n", N, grid, mode, shift,
+           contend, commit_every, cpm, N / 2, 100.0 * (N / 2) / cpm, (double)h[2] / (double)h[0], h[3]);
+}
+
+int main() {
+    long long* dout;
+    cudaMalloc(&dout, 32);
+    cudaMalloc(&g_src, 148 * 4 * 8192);
+    cudaMemset(g_src, 0, 148 * 4 * 8192);
+    cudaMalloc(&g_sink, (1024 + 148 * 4096 * 4) * 4);
+    for (int c : {0, 64, 128}) {
+        run<64>(dout, 148, 3, 1, c, 11);
+        run<128>(dout, 148, 3, 1, c, 11);
+        run<256>(dout, 148, 3, 1, c, 11);
+    }
+    return 0;
+}

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_conv.py -m gpu -x -q -p no:cacheprovider -k "igemm or resample or modulated" 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_gpu_conv.py -m gpu -x -q -p no:cacheprovider -k "generator or discriminator" 2>&1 | tail -15
+for impl in 2 3; do timeout 200 python tools/quick_time.py --res 512 --batch 16 --layers --iters 3 --impl $impl > gpurun_out/s3_layers_impl$impl.txt 2>&1; tail -1 gpurun_out/s3_layers_impl$impl.txt; done
