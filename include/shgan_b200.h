@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SHGAN_B200_ABI_VERSION 1
+#define SHGAN_B200_ABI_VERSION 2
 #define SHGAN_MAX_TAPS 16
 #define SHGAN_MAX_SRC 4
 
@@ -180,6 +180,22 @@ int shgan_normalize_2nd_moment(const float* z, float* y, int B, int D, void* str
  * wsq[o,i] = sum_k w_hat[o,i,k]^2 is precomputed when the weights are packed. */
 int shgan_style_prep(const float* styles, const float* wsq, float* s_hat, float* dcoef,
                      int N, int Ci, int Co, int demod, float pre_scale, void* stream);
+/* shgan_style_prep for every style layer of a forward in one launch.  Layer l reads its raw styles from
+ * raw[n*raw_stride + offset[l] + i], i < ci[l] (the columns of ONE dense call over the concatenated affine weights of
+ * all layers: stylegan.py:266,280,323,331 run on the same input [w ; x_global] whenever ws is a broadcast w), and
+ * writes s_hat[l] [N,ci[l]] and, when demod[l], dcoef[l] [N,co[l]].  block_start is filled in by the library. */
+#define SHGAN_MAX_STYLE_LAYERS 40
+typedef struct {
+    int num_layers;
+    int64_t offset[SHGAN_MAX_STYLE_LAYERS];
+    int ci[SHGAN_MAX_STYLE_LAYERS], co[SHGAN_MAX_STYLE_LAYERS], demod[SHGAN_MAX_STYLE_LAYERS];
+    float pre_scale[SHGAN_MAX_STYLE_LAYERS];
+    const void* wsq[SHGAN_MAX_STYLE_LAYERS];
+    void* s_hat[SHGAN_MAX_STYLE_LAYERS];
+    void* dcoef[SHGAN_MAX_STYLE_LAYERS];
+    int block_start[SHGAN_MAX_STYLE_LAYERS + 1];
+} shgan_style_batch;
+int shgan_style_prep_batched(const float* raw, int64_t raw_stride, int N, const shgan_style_batch* tb, void* stream);
 
 /* ---- Spectral Hint Unit ----------------------------------------------------------------------
  * replaces SHU.forward, lib/model_zoo/shgan.py:312-336 (cuFFT rfftn/irfftn + ~340 ATen calls).

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libshgan_b200.so')
 
 SHGAN_MAX_TAPS = 16
 SHGAN_MAX_SRC = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 vp = C.c_void_p
 fp = C.c_void_p  # float* passed as raw device addresses
@@ -43,6 +43,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+SHGAN_MAX_STYLE_LAYERS = 40
+
+
+class StyleBatch(C.Structure):
+    """shgan_style_batch (include/shgan_b200.h)."""
+    _fields_ = [
+        ('num_layers', i32), ('offset', i64 * SHGAN_MAX_STYLE_LAYERS),
+        ('ci', i32 * SHGAN_MAX_STYLE_LAYERS), ('co', i32 * SHGAN_MAX_STYLE_LAYERS), ('demod', i32 * SHGAN_MAX_STYLE_LAYERS),
+        ('pre_scale', f32 * SHGAN_MAX_STYLE_LAYERS), ('wsq', vp * SHGAN_MAX_STYLE_LAYERS),
+        ('s_hat', vp * SHGAN_MAX_STYLE_LAYERS), ('dcoef', vp * SHGAN_MAX_STYLE_LAYERS),
+        ('block_start', i32 * (SHGAN_MAX_STYLE_LAYERS + 1)),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/shgan_b200.h declares
 SIGNATURES = {
     'shgan_abi_version': (i32, []),
@@ -62,6 +76,7 @@ SIGNATURES = {
     'shgan_dense_fwd': (i32, [fp, i64, i32, fp, i64, fp, fp, fp, i64, i32, i32, i32, f32, f32, i32, f32, f32, f32, vp]),
     'shgan_normalize_2nd_moment': (i32, [fp, fp, i32, i32, vp]),
     'shgan_style_prep': (i32, [fp, fp, fp, fp, i32, i32, i32, i32, f32, vp]),
+    'shgan_style_prep_batched': (i32, [fp, i64, i32, C.POINTER(StyleBatch), vp]),
     'shgan_shu_workspace_bytes': (i64, [i32, i32, i32]),
     'shgan_shu_fwd': (i32, [fp, fp, fp, fp, fp, fp, vp, C.POINTER(fp), i32, i32, i32, i32, i32, vp]),
 }

@@ -139,9 +139,85 @@ dcoef_kernel(const float* __restrict__ s_hat, const float* __restrict__ wsq, flo
     if (lane == 0) dcoef[idx] = rsqrtf(s + 1e-8f);
 }
 
+// All style layers of a forward in ONE launch (shgan_style_prep_batched): the per-layer pair of launches above costs
+// ~40 launches of a few microseconds each per generator call.  Block (layer l, chunk c) recomputes the layer's
+// batch-global scale from the (L2-resident) raw styles -- every block of a layer reduces in the same order, so they all
+// obtain the same bits -- writes its slice of s_hat and 64 demodulation coefficients.
+constexpr int SB_THREADS = 256;
+constexpr int SB_OUT_PER_BLOCK = 64;    // (n, o) pairs per block: 8 warps x 8
+
+__global__ void __launch_bounds__(SB_THREADS)
+style_prep_batched_kernel(const float* __restrict__ raw, long long raw_stride, int N, const shgan_style_batch tb) {
+    __shared__ float red[SB_THREADS / 32];
+    __shared__ float s_sc;
+    int l = 0;
+    while (l + 1 < tb.num_layers && (int)blockIdx.x >= tb.block_start[l + 1]) ++l;
+    const int chunk = blockIdx.x - tb.block_start[l];
+    const int nchunks = tb.block_start[l + 1] - tb.block_start[l];
+    const int Ci = tb.ci[l], Co = tb.co[l], total = N * Ci;
+    const float* rl = raw + tb.offset[l];
+    float sc = tb.pre_scale[l];
+    if (tb.demod[l]) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < total; i += SB_THREADS) {
+            const float v = __ldg(rl + (long long)(i / Ci) * raw_stride + (i % Ci));
+            s = fmaf(v, v, s);
+        }
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+            for (int i = 0; i < SB_THREADS / 32; ++i) tot += red[i];
+            s_sc = rsqrtf(tot / (float)total);
+        }
+        __syncthreads();
+        sc = s_sc;
+    }
+    float* sh = (float*)tb.s_hat[l];
+    for (int i = chunk * SB_THREADS + threadIdx.x; i < total; i += nchunks * SB_THREADS)
+        sh[i] = __ldg(rl + (long long)(i / Ci) * raw_stride + (i % Ci)) * sc;
+    if (!tb.demod[l]) return;
+    const float* wsq = (const float*)tb.wsq[l];
+    float* dc = (float*)tb.dcoef[l];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = 0; k < SB_OUT_PER_BLOCK / 8; ++k) {
+        const long long idx = (long long)chunk * SB_OUT_PER_BLOCK + k * 8 + warp;
+        if (idx >= (long long)N * Co) break;
+        const int n = (int)(idx / Co), o = (int)(idx % Co);
+        float s = 0.f;
+        for (int i = lane; i < Ci; i += 32) {
+            const float v = __ldg(rl + (long long)n * raw_stride + i) * sc;
+            s = fmaf(v * v, __ldg(wsq + (long long)o * Ci + i), s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) dc[idx] = rsqrtf(s + 1e-8f);
+    }
+}
+
 }  // namespace shgan
 
 using namespace shgan;
+
+extern "C" int shgan_style_prep_batched(const float* raw, int64_t raw_stride, int N, const shgan_style_batch* tb_, void* stream) {
+    SHGAN_CHECK(raw && tb_, "null pointer");
+    SHGAN_CHECK(tb_->num_layers >= 1 && tb_->num_layers <= SHGAN_MAX_STYLE_LAYERS, "num_layers out of range");
+    if (N == 0) return 0;
+    shgan_style_batch tb = *tb_;
+    int blocks = 0;
+    for (int l = 0; l < tb.num_layers; ++l) {
+        SHGAN_CHECK(tb.ci[l] >= 1 && tb.s_hat[l], "bad layer description");
+        SHGAN_CHECK(!tb.demod[l] || (tb.wsq[l] && tb.dcoef[l] && tb.co[l] >= 1), "demodulation needs wsq and dcoef");
+        tb.block_start[l] = blocks;
+        const int by_out = tb.demod[l] ? ceil_div(N * tb.co[l], SB_OUT_PER_BLOCK) : 1;
+        const int by_in = ceil_div(N * tb.ci[l], SB_THREADS * 4);
+        blocks += by_out > by_in ? by_out : by_in;
+    }
+    tb.block_start[tb.num_layers] = blocks;
+    style_prep_batched_kernel<<<blocks, SB_THREADS, 0, (cudaStream_t)stream>>>(raw, raw_stride, N, tb);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int shgan_dense_fwd(const float* x0, int64_t x0_stride, int I0, const float* x1, int64_t x1_stride,
                                const float* w, const float* bias, float* y, int64_t y_stride, int B, int I, int O,

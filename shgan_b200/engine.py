@@ -14,6 +14,7 @@ Per-layer mapping of reference ops to launches:
   synthesis conv1 / b4.conv : 1 x shgan_conv_igemm (demod, noise, bias, lrelu, fused torgb, next-layer style)
   torgb + img upsample      : shgan_torgb_combine
 """
+import gc
 import math
 
 import torch
@@ -156,6 +157,18 @@ class GeneratorEngine:
             self.syn[r] = dict(conv0=syn_layer(b.conv0, f'b{r}.conv0', widx), conv1=syn_layer(b.conv1, f'b{r}.conv1', widx + 1),
                                torgb=rgb_layer(b.torgb, f'b{r}.torgb', widx + 2))
             widx += 2
+        # every style affine reads the same input [w ; x_global] when ws is a broadcast w (always, on the eval path:
+        # comodgan.py:449-481 repeats w to num_ws): one dense call over the concatenated weights serves all layers
+        gains = {L['again'] for L in self.style_layers}
+        self.aff_cat = None
+        if len(gains) == 1 and len(self.style_layers) <= 40:
+            off = 0
+            for L in self.style_layers:
+                L['offset'] = off
+                off += L['ci']
+            self.aff_cat = dict(w=torch.cat([L['aw'] for L in self.style_layers], dim=0).contiguous(),
+                                b=torch.cat([L['ab'] for L in self.style_layers], dim=0).contiguous(),
+                                gain=gains.pop(), total=off)
         self._sig = self._signature()
 
     def _ensure(self):
@@ -255,6 +268,19 @@ class GeneratorEngine:
         (stylegan.py:280, 331 and :145-155).  ws [N,num_ws,w_dim] (any strides with unit inner stride)."""
         n = x_global.shape[0]
         out = {}
+        if self.aff_cat is not None and ws.stride(1) == 0:
+            A = self.aff_cat
+            raw = self._f32('st.rawcat', n, A['total'])
+            K.dense(ws[:, 0], A['w'], A['b'], raw, A['gain'], 1.0, False, x1=x_global)
+            layers = []
+            for L in self.style_layers:
+                s_hat = self._f32('st.hat.' + L['name'], n, L['ci'])
+                dcoef = self._f32('st.dc.' + L['name'], n, L['co']) if L['demod'] else None
+                layers.append(dict(offset=L['offset'], ci=L['ci'], co=L['co'], demod=L['demod'], pre_scale=L['pre_scale'],
+                                   wsq=L['wsq'], s_hat=s_hat, dcoef=dcoef))
+                out[L['name']] = (s_hat, dcoef)
+            K.style_prep_batched(raw, layers)
+            return out
         for L in self.style_layers:
             raw = self._f32('st.raw.' + L['name'], n, L['ci'])
             K.dense(ws[:, L['widx']], L['aw'], L['ab'], raw, L['again'], 1.0, False, x1=x_global)
@@ -356,8 +382,16 @@ class GeneratorEngine:
             torch.cuda.synchronize()
             torch.cuda.set_rng_state(rng, self.dev)   # the warm-up must not consume the caller's random stream
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self._forward_eager(xs, zs, noise_mode, composite)
+            # no cyclic garbage collection while the stream is capturing: collecting an unreachable generator/engine of an
+            # earlier call frees CUDA resources (graphs, side-stream blocks), and that invalidates the capture in progress
+            gc_was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph):
+                    out = self._forward_eager(xs, zs, noise_mode, composite)
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
             entry = (graph, xs, zs, out)
             self._graphs[key] = entry
         graph, xs, zs, out = entry

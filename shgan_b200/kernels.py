@@ -233,6 +233,17 @@ def style_prep(styles, wsq, s_hat, dcoef, demod, pre_scale=1.0):
                                    _stream()), 'shgan_style_prep')
 
 
+def style_prep_batched(raw, layers):
+    """raw fp32 [N, S] (row stride raw.stride(0)); layers: list of dicts(offset, ci, co, demod, pre_scale, wsq, s_hat, dcoef)."""
+    tb = _lib.StyleBatch()
+    tb.num_layers = len(layers)
+    for i, L in enumerate(layers):
+        tb.offset[i] = L['offset']; tb.ci[i] = L['ci']; tb.co[i] = L['co']; tb.demod[i] = 1 if L['demod'] else 0
+        tb.pre_scale[i] = L['pre_scale']; tb.wsq[i] = _p(L['wsq']); tb.s_hat[i] = _p(L['s_hat']); tb.dcoef[i] = _p(L['dcoef'])
+    lib = _lib.load()
+    _lib.check(lib.shgan_style_prep_batched(_p(raw), raw.stride(0), raw.shape[0], C.byref(tb), _stream()), 'shgan_style_prep_batched')
+
+
 # ---- SHU -----------------------------------------------------------------------------------------------
 def shu_workspace_bytes(n, c, r):
     return int(_lib.load().shgan_shu_workspace_bytes(n, c, r))

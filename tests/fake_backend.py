@@ -227,6 +227,11 @@ def style_prep(styles, wsq, s_hat, dcoef, demod, pre_scale=1.0):
         s_hat.copy_(styles * pre_scale)
 
 
+def style_prep_batched(raw, layers):
+    for L in layers:
+        style_prep(raw[:, L['offset']:L['offset'] + L['ci']], L['wsq'], L['s_hat'], L['dcoef'], L['demod'], L['pre_scale'])
+
+
 def shu_workspace_bytes(n, c, r):
     return 16
 
@@ -250,6 +255,6 @@ def install(monkeypatch):
     import shgan_b200.engine as E
     for name in ['make_epilogue', 'conv_num_nblocks', 'conv_igemm', 'fir_nhwc', 'nchw_to_planes', 'planes_to_nchw',
                  'planes_add_nchw', 'nhwc_to_nchw_f32', 'fromrgb', 'torgb_combine', 'mbstd_append', 'dense', 'normalize_2nd_moment',
-                 'style_prep', 'shu_workspace_bytes', 'shu_fwd']:
+                 'style_prep', 'style_prep_batched', 'shu_workspace_bytes', 'shu_fwd']:
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(E, '_check_device', lambda dev: None)

@@ -133,6 +133,29 @@ def test_style_prep():
     assert relerr(s_hat.cpu().numpy(), s * 0.25) <= 1e-7
 
 
+def test_style_prep_batched():
+    """All style layers in one launch (columns of one concatenated dense output) == the per-layer entry point."""
+    from shgan_b200 import kernels as K
+    r = np.random.default_rng(41)
+    specs = [(512, 512, True, 1.0), (512, 3, False, 0.044), (64, 128, True, 1.0), (256, 3, False, 0.0625), (128, 64, True, 1.0)]
+    n, total = 7, sum(c for c, _, _, _ in specs)
+    raw = (1 + 0.5 * r.standard_normal((n, total + 8))).astype(np.float32)      # row stride > total
+    raw_t = t(raw)[:, :total]
+    layers, refs, off = [], [], 0
+    for ci, co, demod, ps in specs:
+        wsq = t(r.random((co, ci)).astype(np.float32)) if demod else None
+        L = dict(offset=off, ci=ci, co=co, demod=demod, pre_scale=ps, wsq=wsq, s_hat=torch.empty((n, ci), device=DEV),
+                 dcoef=torch.empty((n, co), device=DEV) if demod else None)
+        sh, dc = torch.empty((n, ci), device=DEV), (torch.empty((n, co), device=DEV) if demod else None)
+        K.style_prep(raw_t[:, off:off + ci].contiguous(), wsq, sh, dc, demod, ps)
+        layers.append(L); refs.append((sh, dc)); off += ci
+    K.style_prep_batched(raw_t, layers)
+    for L, (sh, dc) in zip(layers, refs):
+        assert relerr(L['s_hat'].cpu().numpy(), sh.cpu().numpy()) <= 1e-6
+        if dc is not None:
+            assert relerr(L['dcoef'].cpu().numpy(), dc.cpu().numpy()) <= 2e-6
+
+
 # ---------------------------------------------------------------------------------------------- FIR / pointwise
 def test_fir_nhwc_epilogue_and_parity():
     from shgan_b200 import kernels as K
