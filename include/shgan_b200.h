@@ -124,7 +124,8 @@ typedef struct {
                                         the per-tap kernel for the small ones, chosen per layer;
                                     1 = fp32 FMA kernel with identical operands/epilogue, kept ONLY as the on-device
                                         cross-check of the tensor-core kernels at full layer sizes (tests);
-                                    2 / 3 = force the per-tap / the halo-tile tensor-core kernel (tests, profiling) */
+                                    2 / 3 = force the per-tap / the halo-tile tensor-core kernel (tests, profiling);
+                                    4 = the two-SM (cta_group::2) kernel wherever Co % 256 == 0, per-tap elsewhere */
 } shgan_conv_desc;
 int shgan_conv_igemm(const shgan_conv_desc* d, void* stream);
 /* size of the rgb partial axis: Co / 32 (independent of block_n, kept in the signature for ABI stability) */

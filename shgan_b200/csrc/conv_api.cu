@@ -41,8 +41,14 @@ extern "C" int shgan_conv_igemm(const shgan_conv_desc* d, void* stream_) {
     const ConvGeom g = make_geom(*d);
     const EpiParams epi = d->mode == 0 ? make_epi(d->epi) : EpiParams{};
     if (d->impl == 1) return launch_conv_simt(g, epi, bn, stream);
-    SHGAN_CHECK(d->impl == 0 || d->impl == 2 || d->impl == 3, "impl must be 0, 1, 2 or 3");
+    SHGAN_CHECK(d->impl == 0 || (d->impl >= 2 && d->impl <= 4), "impl must be 0, 1, 2, 3 or 4");
     const int passes = d->passes == 0 ? 3 : d->passes;
+    if (d->impl == 4 && bn == 0 && conv_pair_supported(g)) return launch_conv_pair(g, epi, passes, stream);
+    if (d->impl == 4) return launch_conv_tc(g, epi, bn, passes, stream);
+    // per-layer choice of the product path (impl == 0), from per-layer timings of the three kernels on B200
+    // (profiles/r1_conv_kernel_choice.md): the two-SM kernel wherever Co % 256 == 0 and there are enough tile pairs to
+    // occupy the 74 clusters; the halo kernel for the remaining wide transposed-conv passes; the per-tap kernel elsewhere
+    if (d->impl == 0 && bn == 0 && conv_prefers_pair(g)) return launch_conv_pair(g, epi, passes, stream);
     if (d->impl == 3 || (d->impl == 0 && bn == 0 && conv_prefers_halo(g))) return launch_conv_halo(g, epi, bn, passes, stream);
     return launch_conv_tc(g, epi, bn, passes, stream);
 }

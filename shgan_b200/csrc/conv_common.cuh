@@ -41,6 +41,9 @@ static inline ConvGeom make_geom(const shgan_conv_desc& d) {
 int launch_conv_simt(const ConvGeom& g, const EpiParams& epi, int block_n, cudaStream_t stream);
 int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream);
 int launch_conv_halo(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream);
+int launch_conv_pair(const ConvGeom& g, const EpiParams& epi, int passes, cudaStream_t stream);
+bool conv_pair_supported(const ConvGeom& g);
+bool conv_prefers_pair(const ConvGeom& g);
 double conv_halo_efficiency(const ConvGeom& g);
 bool conv_prefers_halo(const ConvGeom& g);
 

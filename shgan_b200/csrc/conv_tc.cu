@@ -214,7 +214,9 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
 
             // one image per tile (every layer from 16x16 up): stage the per-(sample, channel) epilogue vectors in shared
             // memory and fetch the pixel's noise now, so that the tile's final epilogue needs no dependent L2 round trips
-            const bool staged = ti.TN == 1 && g.mode == 0;
+            // (measured: worth 5-13 % for BN = 64 / 128, whose tiles are short; BN = 256 tiles are long enough to hide the
+            // global-load epilogue and lose 4 % to the two barriers, so they keep it)
+            const bool staged = BN < 256 && ti.TN == 1 && g.mode == 0;
             float nz = 0.f;
             if (staged) {
                 asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");

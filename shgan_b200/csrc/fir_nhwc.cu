@@ -324,12 +324,11 @@ constexpr int F2_IW = F2_W + FIR_T - 1, F2_IH = F2_H + FIR_T - 1;      // 35 x 1
 constexpr int F2_THREADS = 512;
 constexpr int F2_PLANE_BYTES = F2_IH * F2_IW * F2_C * 2;               // 33600
 constexpr int F2_PLANE_STRIDE = ((F2_PLANE_BYTES + 127) / 128) * 128;   // TMA destinations are 128 B aligned
-constexpr int F2_STAGE_BYTES = 2 * F2_PLANE_STRIDE;                    // hi + lo planes, or one fp32 tile
+constexpr int F2_STAGE_BYTES = 2 * F2_PLANE_STRIDE;                    // hi + lo planes
 constexpr int F2_HBUF_BYTES = F2_IH * F2_W * F2_C * 4;                 // 61440
 constexpr int F2_SMEM_BYTES = 2 * F2_STAGE_BYTES + F2_HBUF_BYTES + 128 + 64;
 static_assert((F2_H * F2_W * (F2_C / 4)) % F2_THREADS == 0, "phase B items must divide evenly over the threads");
 
-template <bool IN_F32>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__ f, float gain, int N, int C, int OH, int OW,
                  int pad_x0, int pad_y0, EpiParams epi, int parity_split, FirTiles ft) {
@@ -341,7 +340,7 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
     if (threadIdx.x < FIR_T * FIR_T) s_f[threadIdx.x] = f[threadIdx.x];
     if (threadIdx.x == 0) {
         prefetch_tmap(&maps.a);
-        if (!IN_F32) prefetch_tmap(&maps.b);
+        prefetch_tmap(&maps.b);
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         mbar_fence_init();
@@ -363,7 +362,7 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
         const int cx = tx * F2_W - pad_x0, cy = ty * F2_H - pad_y0;
         mbar_expect_tx(&full[stage], 2 * F2_PLANE_BYTES);
         tma_load_4d(dst, &maps.a, &full[stage], cb * F2_C, cx, cy, n);
-        if (!IN_F32) tma_load_4d(dst + F2_PLANE_STRIDE, &maps.b, &full[stage], cb * F2_C, cx, cy, n);
+        tma_load_4d(dst + F2_PLANE_STRIDE, &maps.b, &full[stage], cb * F2_C, cx, cy, n);
     };
 
     // phase A item decomposition (2 items per thread): 8-channel group, row parity, pixel quad, row pair.  Row parity in
@@ -393,21 +392,14 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
 #pragma unroll
             for (int c = 0; c < FIR_T + 3; ++c) {
                 const int pix = r * F2_IW + q * 4 + c;
-                if (IN_F32) {
-                    const float4* sp = reinterpret_cast<const float4*>(sbase + ((size_t)pix * F2_C + cg * 8) * 4);
-                    const float4 a = sp[0], b = sp[1];
-                    row[c][0] = a.x; row[c][1] = a.y; row[c][2] = a.z; row[c][3] = a.w;
-                    row[c][4] = b.x; row[c][5] = b.y; row[c][6] = b.z; row[c][7] = b.w;
-                } else {
-                    const uint4 h = *reinterpret_cast<const uint4*>(sbase + ((size_t)pix * F2_C + cg * 8) * 2);
-                    const uint4 l = *reinterpret_cast<const uint4*>(sbase + F2_PLANE_STRIDE + ((size_t)pix * F2_C + cg * 8) * 2);
-                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                const uint4 h = *reinterpret_cast<const uint4*>(sbase + ((size_t)pix * F2_C + cg * 8) * 2);
+                const uint4 l = *reinterpret_cast<const uint4*>(sbase + F2_PLANE_STRIDE + ((size_t)pix * F2_C + cg * 8) * 2);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 fa = unpack_h2(hw[i]), fb = unpack_h2(lw[i]);
-                        row[c][2 * i] = fa.x + fb.x;
-                        row[c][2 * i + 1] = fa.y + fb.y;
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const float2 fa = unpack_h2(hw[i]), fb = unpack_h2(lw[i]);
+                    row[c][2 * i] = fa.x + fb.x;
+                    row[c][2 * i + 1] = fa.y + fb.y;
                 }
             }
 #pragma unroll
@@ -522,8 +514,7 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
     static int num_sms = 148;
     if (!attr_set) {
         SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
-        SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_2p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
-        SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_2p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
+        SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
         int dev = 0;
         SHGAN_CUDA(cudaGetDevice(&dev));
         SHGAN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -543,20 +534,11 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
         ft.total = (int)tot;
         FirMaps maps;
         const uint32_t box[4] = {(uint32_t)F2_C, (uint32_t)F2_IW, (uint32_t)F2_IH, 1u};
-        if (in_f32) {
-            if (int e = encode_tmap(&maps.a, in_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-            maps.b = maps.a;
-        } else {
-            if (int e = encode_tmap(&maps.a, in_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-            if (int e = encode_tmap(&maps.b, in_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-        }
+        if (int e = encode_tmap(&maps.a, in_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+        if (int e = encode_tmap(&maps.b, in_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
         const int grid = ft.total < num_sms ? ft.total : num_sms;
-        if (in_f32)
-            fir4x4_2p_kernel<true><<<grid, F2_THREADS, F2_SMEM_BYTES, (cudaStream_t)stream>>>(maps, f, gain, N, C, OH, OW, pad_x0, pad_y0,
-                                                                                            epi, parity_split, ft);
-        else
-            fir4x4_2p_kernel<false><<<grid, F2_THREADS, F2_SMEM_BYTES, (cudaStream_t)stream>>>(maps, f, gain, N, C, OH, OW, pad_x0, pad_y0,
-                                                                                             epi, parity_split, ft);
+        fir4x4_2p_kernel<<<grid, F2_THREADS, F2_SMEM_BYTES, (cudaStream_t)stream>>>(maps, f, gain, N, C, OH, OW, pad_x0, pad_y0, epi,
+                                                                                  parity_split, ft);
         SHGAN_LAUNCH_CHECK();
         skip_rank1 = 1;
     }

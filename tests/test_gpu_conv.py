@@ -17,7 +17,7 @@ import helpers as H  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
-IMPLS = [pytest.param(1, id='simt'), pytest.param(0, id='tc'), pytest.param(2, id='tc_tap'), pytest.param(3, id='tc_halo')]
+IMPLS = [pytest.param(1, id='simt'), pytest.param(0, id='tc'), pytest.param(2, id='tc_tap'), pytest.param(3, id='tc_halo'), pytest.param(4, id='tc_pair')]
 
 
 def t(a):
@@ -53,6 +53,8 @@ SHAPES = [
     (1, 64, 64, 70, 45),     # halo kernel: several tiles in x and y with ragged edges
     (2, 128, 128, 33, 64),   # halo kernel: BN = 128, 2 K slabs
     (1, 256, 192, 40, 40),   # 4 K slabs (chunked accumulation across slabs), Co = 3 x 64
+    (1, 128, 256, 40, 24),   # two-SM kernel: 8 M tiles -> 4 CTA pairs, 2 K slabs
+    (3, 64, 512, 20, 12),    # two-SM kernel: odd number of M tiles (the last pair has an idle half), 2 N blocks
 ]
 
 
@@ -169,6 +171,10 @@ def test_generator_tc_gen256(golden):
 
 def test_generator_tc_halo_gen256(golden):
     _check_generator('gen256', 3, golden, 1e-3)
+
+
+def test_generator_tc_pair_gen256(golden):
+    _check_generator('gen256', 4, golden, 1e-3)        # every Co % 256 == 0 layer (plain, stride-2, up-2 passes) on cta_group::2
 
 
 def test_generator_tc_gen512(golden):
