@@ -134,6 +134,24 @@ __device__ __forceinline__ void store_planes8(__half* __restrict__ hi, __half* _
     *reinterpret_cast<uint4*>(lo + idx) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
+// 16 consecutive channels: one 256-bit store per plane (STG.256, sm_100: a lane's 32 bytes are one full sector, so the
+// store path handles half the sector writes of two 128-bit stores); idx must be a multiple of 16 elements
+__device__ __forceinline__ void store_planes16(__half* __restrict__ hi, __half* __restrict__ lo, long long idx, const float* v) {
+    uint32_t hw[8], lw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        __half h0, l0, h1, l1;
+        split_f32(v[2 * i], h0, l0);
+        split_f32(v[2 * i + 1], h1, l1);
+        hw[i] = pack_h2(h0, h1);
+        lw[i] = pack_h2(l0, l1);
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(hi + idx), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]),
+                 "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7]) : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(lo + idx), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]),
+                 "r"(lw[3]), "r"(lw[4]), "r"(lw[5]), "r"(lw[6]), "r"(lw[7]) : "memory");
+}
+
 __device__ __forceinline__ float lrelu_agc(float v, float alpha, float gain, float clampv) {
     v = (v >= 0.f ? v : v * alpha) * gain;
     if (clampv > 0.f) v = fminf(fmaxf(v, -clampv), clampv);
@@ -215,8 +233,13 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& p, float* v, int
                 v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
             }
         }
+        if (CH % 16 == 0) {
 #pragma unroll
-        for (int i = 0; i < CH; i += 8) store_planes8(p.out_hi, p.out_lo, out_pix * Co + o0 + i, v + i);
+            for (int i = 0; i < CH; i += 16) store_planes16(p.out_hi, p.out_lo, out_pix * Co + o0 + i, v + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) store_planes8(p.out_hi, p.out_lo, out_pix * Co + o0 + i, v + i);
+        }
     }
 }
 

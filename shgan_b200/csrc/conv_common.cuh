@@ -131,8 +131,13 @@ __device__ __forceinline__ void epilogue_apply_staged(const EpiParams& p, const 
             const float4 sc = *reinterpret_cast<const float4*>(stg + 2 * BN + oi + i);
             v[i] *= sc.x; v[i + 1] *= sc.y; v[i + 2] *= sc.z; v[i + 3] *= sc.w;
         }
+        if (CH % 16 == 0) {
 #pragma unroll
-        for (int i = 0; i < CH; i += 8) store_planes8(p.out_hi, p.out_lo, pix * Co + o0 + i, v + i);
+            for (int i = 0; i < CH; i += 16) store_planes16(p.out_hi, p.out_lo, pix * Co + o0 + i, v + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) store_planes8(p.out_hi, p.out_lo, pix * Co + o0 + i, v + i);
+        }
     }
 }
 

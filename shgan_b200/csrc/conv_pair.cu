@@ -11,6 +11,8 @@
 // step that is 32 KB of activations + 32 KB of weights = 42 B/clk, one MMA instruction per 128 clocks issued by a
 // single thread for both SMs, and a 3-deep ring of 64 KB stages instead of 2 x 96 KB.
 //
+// Warp roles per CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + (leader) MMA issuer, warps 4-11 = epilogue (TMEM lane
+// quarter warp & 3, column half (warp - 4) >> 2).
 // Protocol (barrier arrays live at the same shared-memory offsets in both CTAs; "leader" = cluster rank 0):
 //   full[s]   leader only.  Both CTAs' TMA loads complete_tx on the LEADER's barrier (cp.async.bulk.tensor ...
 //             .cta_group::2 with the barrier's shared::cluster address in the leader); the leader's producer arrives once
@@ -29,6 +31,20 @@
 
 namespace shgan {
 
+// Development-only cycle accounting (compile with -DSHGAN_PAIR_PROFILE; tools/pair_profile.py reads it back)
+#ifdef SHGAN_PAIR_PROFILE
+__device__ long long g_pair_prof[148 * 16];
+#define PPROF_DECL long long hp_t0 = 0, hp_acc0 = 0, hp_acc1 = 0, hp_acc2 = 0; const long long hp_start = clock64();
+#define PPROF_BEGIN hp_t0 = clock64();
+#define PPROF_END(k) hp_acc##k += clock64() - hp_t0;
+#define PPROF_STORE(base) { long long* d = g_pair_prof + blockIdx.x * 16 + (base); d[0] = clock64() - hp_start; d[1] = hp_acc0; d[2] = hp_acc1; d[3] = hp_acc2; }
+#else
+#define PPROF_DECL
+#define PPROF_BEGIN
+#define PPROF_END(k)
+#define PPROF_STORE(base)
+#endif
+
 struct PairTmaps {
     CUtensorMap a_hi[SHGAN_MAX_SRC];
     CUtensorMap a_lo[SHGAN_MAX_SRC];
@@ -44,19 +60,24 @@ struct PairTile {
     int total_pairs;            // ceil(m_tiles / 2) * nblk
 };
 
+// 4 non-epilogue warps + 8 epilogue warps (16 epilogue warps with 64 values per thread were measured 3 % slower)
 constexpr int CP_THREADS = 384;
 constexpr int CP_EPI_THREADS = 256;
-constexpr int CP_REGS_DEC = 56, CP_REGS_INC = 224;
+constexpr int CP_COL_SPLIT = CP_EPI_THREADS / 128;      // column slices of the tile, one per epilogue warpgroup
+// setmaxnreg budget: 384 threads are launched with 168 registers (ptxas cap for that block size): 128*56 + 256*224 <= 384*168
+constexpr int CP_REGS_LAUNCH = 168, CP_REGS_DEC = 56, CP_REGS_INC = 224;
+static_assert(128 * CP_REGS_DEC + CP_EPI_THREADS * CP_REGS_INC <= CP_THREADS * CP_REGS_LAUNCH, "setmaxnreg budget exceeds the CTA register pool");
 constexpr int CP_M = 128;            // pixels per CTA (UMMA M = 256 over the pair)
 constexpr int CP_BN = 256;           // output channels per tile (UMMA N)
 constexpr int CP_KC = 64;
-constexpr int CP_MAX_CHUNK = 4;
+constexpr int CP_MAX_CHUNK = 6;
 constexpr int CP_A_BYTES = CP_M * CP_KC * 2;            // 16 KB per plane
 constexpr int CP_B_BYTES = (CP_BN / 2) * CP_KC * 2;     // this CTA's half of the weight tile: 16 KB per plane
 constexpr int CP_STAGE_BYTES = 2 * CP_A_BYTES + 2 * CP_B_BYTES;   // 64 KB
 constexpr int CP_STAGES = 3;
 constexpr int CP_NACC = 2;           // 2 x 256 TMEM columns
-constexpr int CP_SMEM_BYTES = CP_STAGES * CP_STAGE_BYTES + 1024 + 256;
+constexpr int CP_STG_BYTES = CONV_STG_VECS * CP_BN * 4;   // per-tile epilogue vectors (stage_epilogue_vectors)
+constexpr int CP_SMEM_BYTES = CP_STAGES * CP_STAGE_BYTES + 1024 + 256 + CP_STG_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -74,7 +95,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of the 2-CTA form: data lands in THIS CTA's shared memory, the transaction bytes are credited to the barrier at
 // `bar_cluster_addr` (the leader's)
@@ -119,6 +140,7 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
     uint64_t* tfull_bar = bars + 2 * CP_STAGES;          // [NACC]
     uint64_t* tempty_bar = bars + 2 * CP_STAGES + CP_NACC;   // [NACC] (leader's are the live ones)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CP_STAGES + 2 * CP_NACC);
+    float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [CONV_STG_VECS][CP_BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -198,14 +220,19 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            PPROF_DECL
             for (int pt = cluster_id; pt < ti.total_pairs; pt += num_clusters) {
                 for (int it0 = 0; it0 < kiters; it0 += chunk_iters) {
                     const int n_it = kiters - it0 < chunk_iters ? kiters - it0 : chunk_iters;
+                    PPROF_BEGIN
                     mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                    PPROF_END(1)
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CP_BN);
                     for (int it = 0; it < n_it; ++it) {
+                        PPROF_BEGIN
                         mbar_wait(&full_bar[stage], phase);
+                        PPROF_END(0)
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + stage * CP_STAGE_BYTES);
                         const uint32_t a_hi = sa, a_lo = sa + CP_A_BYTES, b_hi = sa + 2 * CP_A_BYTES, b_lo = b_hi + CP_B_BYTES;
@@ -226,12 +253,13 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
                     if (++acc == CP_NACC) { acc = 0; acc_phase ^= 1; }
                 }
             }
+            PPROF_STORE(0)
         }
       }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CP_REGS_INC));
         // ===================== epilogue (warps 4..11 of both CTAs) =====================
-        constexpr int HN = CP_BN / 2;
+        constexpr int HN = CP_BN / CP_COL_SPLIT;
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         const int row = q * 32 + lane;
@@ -241,6 +269,7 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
         const int nchunks = (kiters + chunk_iters - 1) / chunk_iters;
         int acc = 0;
         uint32_t acc_phase = 0;
+        PPROF_DECL
         for (int pt = cluster_id; pt < ti.total_pairs; pt += num_clusters) {
             int m = 2 * (pt / ti.nblk) + (int)rank;
             const int nb = pt % ti.nblk;
@@ -251,9 +280,23 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
             const bool valid = n < g.N && y < g.OH && x < g.OW;
             const long long pix = ((long long)n * g.OH + y) * g.OW + x;
 
+            // one image per tile: stage the per-(sample, channel) epilogue vectors and fetch the pixel's noise now, so that the
+            // tile's final epilogue (during which the MMA issuer can only run CP_NACC chunks ahead) has no dependent L2 trips
+            const bool staged = ti.TN == 1 && g.mode == 0;
+            float nz = 0.f;
+            if (staged) {
+                asm volatile("bar.sync 1, %0;" ::"n"(CP_EPI_THREADS) : "memory");
+                stage_epilogue_vectors<CP_BN, CP_EPI_THREADS>(epi, stg, n, g.Co, nb * CP_BN, (int)threadIdx.x - (CP_THREADS - CP_EPI_THREADS));
+                asm volatile("bar.sync 1, %0;" ::"n"(CP_EPI_THREADS) : "memory");
+                if (epi.noise && valid) nz = __ldg(epi.noise + (long long)n * epi.noise_sn + (long long)y * g.OW + x) * __ldg(epi.noise_strength);
+            }
+
             float accv[HN];
             for (int c = 0; c < nchunks; ++c) {
+                PPROF_BEGIN
                 mbar_wait(&tfull_bar[acc], acc_phase);
+                PPROF_END(0)
+                PPROF_BEGIN
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CP_BN + half * HN);
 #pragma unroll
@@ -266,14 +309,18 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+                PPROF_END(1)
                 if (++acc == CP_NACC) { acc = 0; acc_phase ^= 1; }
             }
+            PPROF_BEGIN
             if (valid) {
                 float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                 for (int p = 0; p < HN / 16; ++p) {
-                    const int o0 = nb * CP_BN + half * HN + p * 16;
+                    const int oi = half * HN + p * 16;
+                    const int o0 = nb * CP_BN + oi;
                     if (g.mode == 1) raw_store<16>(g, accv + p * 16, n, y, x, o0);
+                    else if (staged) epilogue_apply_staged<CP_BN, 16>(epi, stg, accv + p * 16, nz, g.Co, o0, oi, rgb, pix);
                     else epilogue_apply<16>(epi, accv + p * 16, n, y, x, g.OH, g.OW, g.Co, o0, rgb, pix);
                     if ((p & 1) && g.mode == 0 && epi.rgb_w) {
                         float* dst = epi.rgb_out + (pix * (g.Co / CONV_RGB_BLOCK) + (o0 - 16) / CONV_RGB_BLOCK) * 4;
@@ -282,7 +329,11 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
                     }
                 }
             }
+            PPROF_END(2)
         }
+#ifdef SHGAN_PAIR_PROFILE
+        if (threadIdx.x == CP_THREADS - CP_EPI_THREADS) PPROF_STORE(4)
+#endif
     }
 
     tc_fence_before();
@@ -368,3 +419,9 @@ int launch_conv_pair(const ConvGeom& g, const EpiParams& epi, int passes, cudaSt
 }
 
 }  // namespace shgan
+
+#ifdef SHGAN_PAIR_PROFILE
+extern "C" int shgan_debug_pair_profile(long long* host_out /*[148*16]*/) {
+    return (int)cudaMemcpyFromSymbol(host_out, shgan::g_pair_prof, sizeof(long long) * 148 * 16);
+}
+#endif
