@@ -68,16 +68,19 @@ constexpr int CP_COL_SPLIT = CP_EPI_THREADS / 128;      // column slices of the 
 constexpr int CP_REGS_LAUNCH = 168, CP_REGS_DEC = 56, CP_REGS_INC = 224;
 static_assert(128 * CP_REGS_DEC + CP_EPI_THREADS * CP_REGS_INC <= CP_THREADS * CP_REGS_LAUNCH, "setmaxnreg budget exceeds the CTA register pool");
 constexpr int CP_M = 128;            // pixels per CTA (UMMA M = 256 over the pair)
-constexpr int CP_BN = 256;           // output channels per tile (UMMA N)
 constexpr int CP_KC = 64;
-constexpr int CP_MAX_CHUNK = 6;
 constexpr int CP_A_BYTES = CP_M * CP_KC * 2;            // 16 KB per plane
-constexpr int CP_B_BYTES = (CP_BN / 2) * CP_KC * 2;     // this CTA's half of the weight tile: 16 KB per plane
-constexpr int CP_STAGE_BYTES = 2 * CP_A_BYTES + 2 * CP_B_BYTES;   // 64 KB
-constexpr int CP_STAGES = 3;
-constexpr int CP_NACC = 2;           // 2 x 256 TMEM columns
-constexpr int CP_STG_BYTES = CONV_STG_VECS * CP_BN * 4;   // per-tile epilogue vectors (stage_epilogue_vectors)
-constexpr int CP_SMEM_BYTES = CP_STAGES * CP_STAGE_BYTES + 1024 + 256 + CP_STG_BYTES;
+
+// BN = output channels per tile (UMMA N): 256 for the 256/512-channel layers, 128 for the 128-channel ones
+template <int BN> struct PairCfg {
+    static constexpr int B_BYTES = (BN / 2) * CP_KC * 2;            // this CTA's half of the weight tile, per plane
+    static constexpr int STAGE_BYTES = 2 * CP_A_BYTES + 2 * B_BYTES;   // 64 KB (BN = 256) / 48 KB (BN = 128)
+    static constexpr int STAGES = BN == 256 ? 3 : 4;
+    static constexpr int NACC = 512 / BN;                            // TMEM accumulator buffers
+    static constexpr int MAX_CHUNK = BN == 256 ? 6 : 4;              // (tap, slab) steps chained in one TMEM accumulator
+    static constexpr int STG_BYTES = CONV_STG_VECS * BN * 4;         // per-tile epilogue vectors (stage_epilogue_vectors)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + STG_BYTES;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -129,9 +132,12 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
                  : "memory");
 }
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const EpiParams epi, const PairTile ti, const int passes,
                  const int chunk_iters) {
+    using Cfg = PairCfg<BN>;
+    constexpr int CP_BN = BN, CP_STAGES = Cfg::STAGES, CP_NACC = Cfg::NACC, CP_STAGE_BYTES = Cfg::STAGE_BYTES, CP_B_BYTES = Cfg::B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CP_STAGES * CP_STAGE_BYTES);
@@ -352,7 +358,8 @@ static int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uin
 static int pow2_ceil_i(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int ilog2_i(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-bool conv_pair_supported(const ConvGeom& g) { return g.Co % CP_BN == 0 && g.C % CP_KC == 0; }
+static int pair_bn(const ConvGeom& g) { return g.Co % 256 == 0 ? 256 : 128; }
+bool conv_pair_supported(const ConvGeom& g) { return g.Co % 128 == 0 && g.C % CP_KC == 0; }
 
 // enough 256-pixel x 256-channel tiles for (nearly) every cluster: measured faster than the single-CTA kernels from 32 x 32
 // x batch 16 upwards (-15 .. -18 % on the 256- and 512-channel layers), slower below (4 x 4 .. 16 x 16: too few pairs)
@@ -362,11 +369,34 @@ bool conv_prefers_pair(const ConvGeom& g) {
     const int th = pow2_ceil_i(g.OH) < CP_M / tw ? pow2_ceil_i(g.OH) : CP_M / tw;
     const int tn = CP_M / (tw * th);
     const long long m_tiles = (long long)ceil_div(g.OW, tw) * ceil_div(g.OH, th) * ceil_div(g.N, tn);
-    return ((m_tiles + 1) / 2) * (g.Co / CP_BN) >= 64;
+    return ((m_tiles + 1) / 2) * (g.Co / pair_bn(g)) >= 64;
+}
+
+template <int BN>
+static int launch_pair_bn(const PairTmaps& maps, const ConvGeom& g, const EpiParams& epi, const PairTile& ti, int passes, cudaStream_t stream) {
+    using Cfg = PairCfg<BN>;
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
+        SHGAN_CUDA(cudaFuncSetAttribute(conv_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        int dev = 0;
+        SHGAN_CUDA(cudaGetDevice(&dev));
+        SHGAN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    const int max_clusters = num_sms / 2;
+    const int clusters = ti.total_pairs < max_clusters ? ti.total_pairs : max_clusters;
+    const int kiters = g.ntaps * (g.C / CP_KC);
+    const int nchunks = ceil_div(kiters, Cfg::MAX_CHUNK);
+    const int chunk_iters = ceil_div(kiters, nchunks);
+    conv_pair_kernel<BN><<<2 * clusters, CP_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, g, epi, ti, passes, chunk_iters);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_conv_pair(const ConvGeom& g, const EpiParams& epi, int passes, cudaStream_t stream) {
-    SHGAN_CHECK(conv_pair_supported(g), "the two-SM kernel needs Co % 256 == 0 and C % 64 == 0");
+    SHGAN_CHECK(conv_pair_supported(g), "the two-SM kernel needs Co % 128 == 0 and C % 64 == 0");
+    const int CP_BN = pair_bn(g);
     SHGAN_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
     PairTile ti;
     ti.TW = pow2_ceil_i(g.OW) < 16 ? pow2_ceil_i(g.OW) : 16;
@@ -399,23 +429,8 @@ int launch_conv_pair(const ConvGeom& g, const EpiParams& epi, int passes, cudaSt
     if (int e = encode_map_f16(&maps.w_hi, g.w_hi, 2, wdims, wbox)) return e;
     if (int e = encode_map_f16(&maps.w_lo, g.w_lo, 2, wdims, wbox)) return e;
 
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
-        SHGAN_CUDA(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES));
-        int dev = 0;
-        SHGAN_CUDA(cudaGetDevice(&dev));
-        SHGAN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
-    const int max_clusters = num_sms / 2;
-    const int clusters = ti.total_pairs < max_clusters ? ti.total_pairs : max_clusters;
-    const int kiters = g.ntaps * (g.C / CP_KC);
-    const int nchunks = ceil_div(kiters, CP_MAX_CHUNK);
-    const int chunk_iters = ceil_div(kiters, nchunks);
-    conv_pair_kernel<<<2 * clusters, CP_THREADS, CP_SMEM_BYTES, stream>>>(maps, g, epi, ti, passes, chunk_iters);
-    SHGAN_LAUNCH_CHECK();
-    return 0;
+    if (CP_BN == 256) return launch_pair_bn<256>(maps, g, epi, ti, passes, stream);
+    return launch_pair_bn<128>(maps, g, epi, ti, passes, stream);
 }
 
 }  // namespace shgan

@@ -23,6 +23,22 @@ constexpr int FIR_SX = 2;    // output pixels per thread along x
 constexpr int FIR_TY = 16;   // output rows per thread
 constexpr int FIR_THREADS = 128;
 
+// explicit shared-state-space accesses on 32-bit addresses: after the 128-byte alignment cast the compiler no longer
+// knows the dynamic buffer is shared memory and emits generic LD/ST with 64-bit address arithmetic
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // rank-1 factorisation of the 4x4 filter around its largest tap; true when |f - u (x) v| <= 1e-6 max|f|
 __device__ __forceinline__ bool fir_factorise(const float* sf, float* u, float* v) {
     int bi = 0, bj = 0;
@@ -381,7 +397,7 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
         const int ty = t % ft.tiles_y;
         const int n = t / ft.tiles_y;
         mbar_wait(&full[stage], (it >> 1) & 1);
-        const uint8_t* sbase = smem + stage * F2_STAGE_BYTES;
+        const uint32_t sbase = smem_u32(smem) + stage * F2_STAGE_BYTES, hb = smem_u32(hbuf);
 
         // ---------------- phase A: horizontal pass -> hbuf ----------------
 #pragma unroll 1
@@ -392,8 +408,8 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
 #pragma unroll
             for (int c = 0; c < FIR_T + 3; ++c) {
                 const int pix = r * F2_IW + q * 4 + c;
-                const uint4 h = *reinterpret_cast<const uint4*>(sbase + ((size_t)pix * F2_C + cg * 8) * 2);
-                const uint4 l = *reinterpret_cast<const uint4*>(sbase + F2_PLANE_STRIDE + ((size_t)pix * F2_C + cg * 8) * 2);
+                const uint4 h = lds128(sbase + (pix * F2_C + cg * 8) * 2);
+                const uint4 l = lds128(sbase + F2_PLANE_STRIDE + (pix * F2_C + cg * 8) * 2);
                 const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -412,9 +428,9 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
                     a = fmaf(row[ox + 2][j], v[2], a);
                     h[j] = fmaf(row[ox + 3][j], v[3], a);
                 }
-                float4* dst = reinterpret_cast<float4*>(hbuf + ((size_t)(r * F2_W + q * 4 + ox) * F2_C + cg * 8));
-                dst[0] = make_float4(h[0], h[1], h[2], h[3]);
-                dst[1] = make_float4(h[4], h[5], h[6], h[7]);
+                const uint32_t dst = hb + ((r * F2_W + q * 4 + ox) * F2_C + cg * 8) * 4;
+                sts128f(dst, h[0], h[1], h[2], h[3]);
+                sts128f(dst + 16, h[4], h[5], h[6], h[7]);
             }
         }
         __syncthreads();
@@ -435,32 +451,32 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
                 }
             }
             const float nstr = epi.noise ? __ldg(epi.noise_strength) : 0.f;
+            // element indices fit in 32 bits (checked on the host): plain int arithmetic, one widening per access
+            const bool xin = x < OW;
+            const int plane = N * PH * PW;                                    // parity_split == 1: pixels per parity plane
+            const uint32_t hcol = hb + (b_px * F2_C + b_g4 * 4) * 4;
 #pragma unroll 2
             for (int jr = threadIdx.x / (F2_W * (F2_C / 4)); jr < F2_H; jr += F2_THREADS / (F2_W * (F2_C / 4))) {
                 const int yo = y0 + jr;
-                if (yo < OH && x < OW && !(parity_split == 2 && ((yo | x) & 1))) {
-                    const long long pix = ((long long)n * OH + yo) * OW + x;
+                if (yo < OH && xin && !(parity_split == 2 && ((yo | x) & 1))) {
+                    const int pix = (n * OH + yo) * OW + x;
                     float nz = 0.f;
                     uint2 sh = make_uint2(0u, 0u), sl = make_uint2(0u, 0u);
-                    if (epi.noise) nz = __ldg(epi.noise + (long long)n * epi.noise_sn + (long long)yo * OW + x) * nstr;
+                    if (epi.noise) nz = __ldg(epi.noise + (long long)n * epi.noise_sn + yo * OW + x) * nstr;
                     if (epi.skip_hi) {
-                        sh = __ldg(reinterpret_cast<const uint2*>(epi.skip_hi + pix * C + c0));
-                        sl = __ldg(reinterpret_cast<const uint2*>(epi.skip_lo + pix * C + c0));
+                        sh = __ldg(reinterpret_cast<const uint2*>(epi.skip_hi + (size_t)(pix * C + c0)));
+                        sl = __ldg(reinterpret_cast<const uint2*>(epi.skip_lo + (size_t)(pix * C + c0)));
                     }
                     float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int k = 0; k < FIR_T; ++k) {
-                        const float4 hv = *reinterpret_cast<const float4*>(hbuf + ((size_t)((jr + k) * F2_W + b_px) * F2_C + b_g4 * 4));
+                        const float4 hv = lds128f(hcol + (jr + k) * (F2_W * F2_C * 4));
                         o[0] = fmaf(hv.x, u[k], o[0]); o[1] = fmaf(hv.y, u[k], o[1]);
                         o[2] = fmaf(hv.z, u[k], o[2]); o[3] = fmaf(hv.w, u[k], o[3]);
                     }
-                    long long out_pix = pix;
-                    if (parity_split == 1) {
-                        const int qd = (yo & 1) * 2 + (x & 1);
-                        out_pix = (long long)qd * N * PH * PW + ((long long)n * PH + (yo >> 1)) * PW + (x >> 1);
-                    } else if (parity_split == 2) {
-                        out_pix = ((long long)n * PH + (yo >> 1)) * PW + (x >> 1);
-                    }
+                    int out_pix = pix;
+                    if (parity_split == 1) out_pix = ((yo & 1) * 2 + (x & 1)) * plane + (n * PH + (yo >> 1)) * PW + (x >> 1);
+                    else if (parity_split == 2) out_pix = (n * PH + (yo >> 1)) * PW + (x >> 1);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) o[j] = o[j] * e_dc[j] + nz + e_b[j];
                     if (epi.act) {
@@ -474,13 +490,14 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
                         const float2 h0 = unpack_h2(sh.x), h1 = unpack_h2(sh.y), l0 = unpack_h2(sl.x), l1 = unpack_h2(sl.y);
                         o[0] += h0.x + l0.x; o[1] += h0.y + l0.y; o[2] += h1.x + l1.x; o[3] += h1.y + l1.y;
                     }
-                    if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + out_pix * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
+                    const size_t oidx = (size_t)(out_pix * C + c0);
+                    if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + oidx) = make_float4(o[0], o[1], o[2], o[3]);
                     if (epi.out_hi) {
                         __half hh[4], ll[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) split_f32(o[j] * e_nx[j], hh[j], ll[j]);
-                        *reinterpret_cast<uint2*>(epi.out_hi + out_pix * C + c0) = make_uint2(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]));
-                        *reinterpret_cast<uint2*>(epi.out_lo + out_pix * C + c0) = make_uint2(pack_h2(ll[0], ll[1]), pack_h2(ll[2], ll[3]));
+                        *reinterpret_cast<uint2*>(epi.out_hi + oidx) = make_uint2(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]));
+                        *reinterpret_cast<uint2*>(epi.out_lo + oidx) = make_uint2(pack_h2(ll[0], ll[1]), pack_h2(ll[2], ll[3]));
                     }
                 }
             }

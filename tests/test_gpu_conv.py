@@ -55,6 +55,8 @@ SHAPES = [
     (1, 256, 192, 40, 40),   # 4 K slabs (chunked accumulation across slabs), Co = 3 x 64
     (1, 128, 256, 40, 24),   # two-SM kernel: 8 M tiles -> 4 CTA pairs, 2 K slabs
     (3, 64, 512, 20, 12),    # two-SM kernel: odd number of M tiles (the last pair has an idle half), 2 N blocks
+    (2, 128, 128, 24, 24),   # two-SM kernel, BN = 128 (four TMEM accumulator buffers)
+    (1, 64, 384, 17, 30),    # two-SM kernel, BN = 128, 3 N blocks, ragged tiles
 ]
 
 
