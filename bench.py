@@ -9,8 +9,9 @@ the forward needs no collective).  Rank 0 prints ONE JSON line:
   value        images/s, inputs already resident in HBM, CUDA-event timed, max over ranks
   e2e          same metric through the public module API with pinned-host inputs: H2D copy of (x, z) and D2H read of the
                uint8 composite inside the timed region
-  roofline     the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOP/s measured with CUDA events around every
-               launch inside the timed region, against the measured bf16 tensor peak of MEASURED_PEAKS.json
+  roofline     the dominant kernel (the tcgen05 implicit-GEMM convolution behind shgan_conv_igemm): algorithmic FLOP/s measured
+               with CUDA events around every launch, against the measured bf16 tensor peak of MEASURED_PEAKS.json (the
+               profiling guide's fallback when the driver has not written that file; `peak_source` says which)
   cpu_baseline the CPU oracle (a port of the reference's PyTorch CPU path; the reference is Python and cannot be compiled
                into oracle/_ref) timed on the host cores on a bounded sample
 `--impl reference` times that CPU implementation alone, as the reference arm.
@@ -301,7 +302,7 @@ def main():
                      api='model_zoo.comodgan.Generator.forward_composite(x, z); pinned host batches in, uint8 composites read back to pinned host; '
                          'H2D/D2H on a copy stream, 2-deep pipeline, all copies inside the timed region'),
             gpu_launches=int(launches),
-            roofline=dict(bound='tensor', kernel='shgan::conv_tc_kernel (tcgen05 implicit-GEMM conv, all layer shapes)',
+            roofline=dict(bound='tensor', kernel='shgan_conv_igemm: conv_pair_kernel (tcgen05 cta_group::2, Co % 128 == 0) + conv_tc_kernel / conv_halo_kernel (single-CTA tcgen05), all 51 conv launches of a step',
                           achieved=conv_tflops, peak=peaks['tensor'], unit='TFLOP/s', frac=conv_tflops / peaks['tensor'],
                           traffic=traffic, peak_source=f'{peaks["src"]} bf16 sustained', launches_per_step=n_conv // max(args.steps, 1),
                           algorithmic_gflop_per_step=conv_flops[0] / max(args.steps, 1) / 1e9,

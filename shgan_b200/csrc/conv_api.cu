@@ -46,7 +46,7 @@ extern "C" int shgan_conv_igemm(const shgan_conv_desc* d, void* stream_) {
     if (d->impl == 4 && bn == 0 && conv_pair_supported(g)) return launch_conv_pair(g, epi, passes, stream);
     if (d->impl == 4) return launch_conv_tc(g, epi, bn, passes, stream);
     // per-layer choice of the product path (impl == 0), from per-layer timings of the three kernels on B200
-    // (profiles/r1_conv_kernel_choice.md): the two-SM kernel wherever Co % 256 == 0 and there are enough tile pairs to
+    // (profiles/r1_conv_findings.md section 4): the two-SM kernel wherever Co % 128 == 0 and there are enough tile pairs to
     // occupy the 74 clusters; the halo kernel for the remaining wide transposed-conv passes; the per-tap kernel elsewhere
     if (d->impl == 0 && bn == 0 && conv_prefers_pair(g)) return launch_conv_pair(g, epi, passes, stream);
     if (d->impl == 3 || (d->impl == 0 && bn == 0 && conv_prefers_halo(g))) return launch_conv_halo(g, epi, bn, passes, stream);

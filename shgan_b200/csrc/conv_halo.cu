@@ -454,12 +454,12 @@ double conv_halo_efficiency(const ConvGeom& g) {
     return eff;
 }
 
-// Layer-level choice between the two tensor-core kernels (impl == 0), from per-layer timings of both kernels on B200
-// (profiles/r1_conv_kernel_choice.md).  Both kernels are bound by the rate at which ONE thread can issue tcgen05.mma
-// (~70-90 clocks per instruction once barrier waits and descriptor set-up are in the loop), which only N = 256 tiles hide:
-// the per-tap kernel (BN up to 256) therefore wins wherever Co >= 256 or the halo waste is large, and the halo kernel
-// wins for the wide transposed-convolution passes at 17^2 .. 65^2, whose 1-4 tap K loops are too short to amortise the
-// per-tap kernel's per-tile operand latency.
+// Halo vs per-tap kernel for the layers the two-SM kernel does not take (impl == 0), from per-layer timings on B200
+// (profiles/r1_conv_findings.md section 4).  Both single-CTA kernels are bound by the rate at which ONE thread can issue
+// tcgen05.mma (~70-90 clocks per instruction once barrier waits and descriptor set-up are in the loop), which only N = 256
+// tiles hide: the per-tap kernel (BN up to 256) wins wherever the halo waste is large, and the halo kernel wins for the wide
+// transposed-convolution passes at 17^2 .. 65^2 (too few tile pairs for the two-SM kernel at 17^2), whose 1-4 tap K loops
+// are too short to amortise the per-tap kernel's per-tile operand latency.
 bool conv_prefers_halo(const ConvGeom& g) {
     if (g.mode != 1 || g.num_src != 1 || g.C < 512 || g.ntaps < 2) return false;
     if (g.OW < 17 || g.OW > 65 || g.OH < 17 || g.OH > 65) return false;
