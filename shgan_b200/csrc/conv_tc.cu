@@ -314,13 +314,20 @@ int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int pas
     ti.tiles_y = ceil_div(g.OH, ti.TH);
     ti.tiles_n = ceil_div(g.N, ti.TN);
     if (block_n == 0) {
-        // widest tile the layer allows (least operand re-fetch), narrowed while the grid cannot fill the SMs:
-        // small-resolution layers are bound by the serial K loop of a tile, not by bandwidth
+        // tile width by a two-term cost model: waves of tiles over the SMs x clocks per MMA.  One thread issues an MMA every
+        // ~90 clocks at best (profiles/r1_conv_findings.md section 2), so N = 64 and N = 128 instructions cost the same and
+        // only N = 256 is bound by the tensor pipe (128 clk): the widest tile wins on large layers (least operand re-fetch,
+        // fewest instructions), and on the 4x4 .. 16x16 layers the width that needs the fewest waves does.
         int dev = 0, num_sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        block_n = conv_block_n(g.Co, 0);
         const long long mt = (long long)ti.tiles_x * ti.tiles_y * ti.tiles_n;
-        while (block_n > 64 && mt * (g.Co / block_n) < num_sms) block_n >>= 1;
+        long long best_cost = -1;
+        for (int bn = conv_block_n(g.Co, 0); bn >= 64; bn >>= 1) {
+            if (g.Co % bn) continue;
+            const long long waves = (mt * (g.Co / bn) + num_sms - 1) / num_sms;
+            const long long cost = waves * (bn / 2 > 90 ? bn / 2 : 90);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; block_n = bn; }   // ties: more, narrower tiles
+        }
     }
     SHGAN_CHECK(g.Co % block_n == 0, "Co must be a multiple of block_n");
     ti.nblk = g.Co / block_n;
