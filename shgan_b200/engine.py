@@ -48,7 +48,9 @@ class GeneratorEngine:
         self.G = G
         self.passes = passes
         self.impl = impl
-        self.graphs = graphs      # replay the ~170 launches of a forward as one CUDA graph per (shape, mode)
+        self.graphs = graphs      # replay the ~120 launches of a forward as one CUDA graph per (shape, mode)
+        self.overlap = True       # run the small off-critical-path kernels (mapping, SHU, torgb combine) on a side stream
+        self._side = None
         self._sig = None
         self._buf = {}
         self._graphs = {}
@@ -177,6 +179,39 @@ class GeneratorEngine:
             self._buf = {}
             self._graphs = {}     # captured graphs reference the old packed operands
 
+    # ---- side stream ---------------------------------------------------------------------------------
+    class _Fork:
+        """`with engine._fork():` runs the enclosed launches on the engine's side stream, ordered after everything already
+        enqueued on the caller's stream; `engine._join()` makes the caller's stream wait for them.  Inside a CUDA-graph
+        capture these become fork / join edges of the graph.  The kernels moved there are latency-bound launches that sit
+        between two large convolutions of the main chain (mapping: 9 launches; the SHU: 4; torgb_combine: 8)."""
+
+        def __init__(self, eng):
+            self.eng = eng
+            self.ctx = None
+
+        def __enter__(self):
+            if not self.eng.overlap or self.eng.dev.type != 'cuda':
+                return self
+            if self.eng._side is None:
+                self.eng._side = torch.cuda.Stream(device=self.eng.dev)
+            self.eng._side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.eng._side)
+            self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            if self.ctx is not None:
+                self.ctx.__exit__(*exc)
+            return False
+
+    def _fork(self):
+        return GeneratorEngine._Fork(self)
+
+    def _join(self):
+        if self.overlap and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+
     # ---- buffers --------------------------------------------------------------------------------------
     def _planes(self, name, n, h, w, c):
         key = (name, n, h, w, c)
@@ -224,6 +259,7 @@ class GeneratorEngine:
         feats = {}
         a = None
         ident = None
+        shu_outs = None
         for r in self.enc_res[:-1]:
             d = self.enc[r]
             c = d['conv0']['ci']
@@ -233,6 +269,9 @@ class GeneratorEngine:
             feat = self._planes(f'e{r}.feat', n, r, r, d['conv0']['co'])
             self._conv([a], d['conv0'], P.taps_plain(3, 3), r, r, epi=self._enc_epi(d['conv0'], feat))
             feats[r] = feat
+            if self.shu is not None and r == self.shu['input_res']:
+                with self._fork():                      # overlaps the rest of the encoder; its outputs are added after the join
+                    shu_outs = self._shu_compute(feat, n)
             # conv1: blur (pad 2) into four parity planes, then the stride-2 conv as a 4-source stride-1 conv
             ph = (r + 1 + 1) // 2
             c1 = d['conv1']['ci']
@@ -249,19 +288,26 @@ class GeneratorEngine:
         flat = K.planes_to_nchw(feat4, out=self._f32('e4.flat', n, d['conv']['co'], 4, 4))
         x_global = self._dense(d['fc'], flat.view(n, -1), self._f32('x_global', n, d['fc'][0].shape[0]))
         if self.shu is not None:
-            s = self.shu
-            ch, rin = s['ch'], s['input_res']
-            fin = feats[rin]
-            xin = K.planes_to_nchw(fin, c_off=fin.shape[3] - ch, c=ch, out=self._f32('shu.in', n, ch, rin, rin))
-            outs = [self._f32(f'shu.out{r}', n, ch, r, r) for r in s['reslist']]
-            ws = self._buf.get(('shu.ws', n))
-            if ws is None:
-                ws = torch.empty(K.shu_workspace_bytes(n, ch, rin), dtype=torch.uint8, device=self.dev)
-                self._buf[('shu.ws', n)] = ws
-            K.shu_fwd(xin, s['conv0_w'], s['conv0_b'], s['df1_w'], s['cw'], s['gauss'], outs, s['lowest_res'], workspace=ws)
-            for r, o in zip(s['reslist'], outs):
+            if shu_outs is None:                        # input_res == 4: the SHU input is the last encoder feature
+                shu_outs = self._shu_compute(feats[self.shu['input_res']], n)
+            self._join()
+            ch = self.shu['ch']
+            for r, o in zip(self.shu['reslist'], shu_outs):
                 K.planes_add_nchw(feats[r], o, feats[r].shape[3] - ch)   # feats[r][:, -ch:] += shu[r]  (shgan.py:378-382)
         return x_global, feats
+
+    def _shu_compute(self, fin, n):
+        """SHU.forward (shgan.py:312-336) on the last `ch` channels of feats[input_res] -> list of fp32 [N,ch,r,r]."""
+        s = self.shu
+        ch, rin = s['ch'], s['input_res']
+        xin = K.planes_to_nchw(fin, c_off=fin.shape[3] - ch, c=ch, out=self._f32('shu.in', n, ch, rin, rin))
+        outs = [self._f32(f'shu.out{r}', n, ch, r, r) for r in s['reslist']]
+        ws = self._buf.get(('shu.ws', n))
+        if ws is None:
+            ws = torch.empty(K.shu_workspace_bytes(n, ch, rin), dtype=torch.uint8, device=self.dev)
+            self._buf[('shu.ws', n)] = ws
+        K.shu_fwd(xin, s['conv0_w'], s['conv0_b'], s['df1_w'], s['cw'], s['gauss'], outs, s['lowest_res'], workspace=ws)
+        return outs
 
     def styles(self, ws, x_global):
         """Affine transforms + style normalisation / demodulation coefficients for every synthesis layer
@@ -353,10 +399,12 @@ class GeneratorEngine:
             img_r = self._f32(f's{r}.img', n, 3, r, r)
             if r == last and comp_x is not None:
                 comp = torch.empty((n, 3, r, r), dtype=torch.uint8, device=self.dev)
-            K.torgb_combine(img, part, d['torgb']['bias'], self.f, img_r, comp_x=comp_x if r == last else None,
-                            comp_out=comp if r == last else None)
+            with self._fork():                          # the image chain only meets the feature chain again at the very end
+                K.torgb_combine(img, part, d['torgb']['bias'], self.f, img_r, comp_x=comp_x if r == last else None,
+                                comp_out=comp if r == last else None)
             img = img_r
             x = out
+        self._join()
         return (img, comp) if comp_x is not None else img
 
     def forward(self, x, z, noise_mode='random', composite=False):
@@ -401,11 +449,14 @@ class GeneratorEngine:
         return out
 
     def _forward_eager(self, x, z, noise_mode='random', composite=False):
-        w = self.mapping(z)
+        self._ensure()
+        with self._fork():                              # the mapping network only meets the encoder at the style affines
+            w = self.mapping(z)
         num_ws = self.G.num_ws
         ws = w.unsqueeze(1).expand(w.shape[0], num_ws, w.shape[1])
         x = x.contiguous().float()
         x_global, feats = self.encoder(x)
+        self._join()
         return self.synthesis(x_global, feats, ws, noise_mode=noise_mode, comp_x=x if composite else None)
 
 
