@@ -60,3 +60,11 @@ def test_sass_has_tcgen05_and_tma():
     sass = subprocess.run([cuobjdump, '-sass', obj], capture_output=True, text=True).stdout
     for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG'):
         assert mnemonic in sass, mnemonic
+    # issue paths run under elect.sync: no per-active-lane waterfall loop around the MMA / TMA instructions
+    assert 'BRA.U.ANY' not in sass
+    # the two-SM kernel: cta_group::2 MMAs, 2-CTA TMA loads, multicast commit, cluster barrier
+    pair = subprocess.run([cuobjdump, '-sass', os.path.join(os.path.dirname(obj), 'conv_pair.o')], capture_output=True, text=True).stdout
+    for mnemonic in ('UTCHMMA.2CTA', 'UTMALDG.4D.2CTA', 'UTCBAR.2CTA.MULTICAST', 'UCGABAR_ARV', 'STG.E.ENL2.256'):
+        assert mnemonic in pair, mnemonic
+    halo = subprocess.run([cuobjdump, '-sass', os.path.join(os.path.dirname(obj), 'conv_halo.o')], capture_output=True, text=True).stdout
+    assert 'UTCHMMA' in halo and 'BRA.U.ANY' not in halo
