@@ -19,6 +19,10 @@ struct ConvGeom {
     int mode;  // 0: epilogue, 1: raw fp32 scatter into z
     float* z;
     int ZH, ZW, zsy, zsx, zoy, zox;
+    // library-internal (not in the C ABI; conv_tc.cu only): per-tap, per-pixel weights of the accumulation,
+    // acc[n,y,x,o] = sum_t chunk_scale[t, y*OW + x] * (tap t's contribution).  Used by the SHU's heterogeneous filter
+    // (shu.cu), whose blend over 6 anchor filters is exactly that.  NULL: plain sum.
+    const float* chunk_scale;
 };
 
 static inline ConvGeom make_geom(const shgan_conv_desc& d) {
@@ -35,6 +39,7 @@ static inline ConvGeom make_geom(const shgan_conv_desc& d) {
     }
     g.OH = d.OH; g.OW = d.OW; g.mode = d.mode; g.z = d.z; g.ZH = d.ZH; g.ZW = d.ZW;
     g.zsy = d.zsy; g.zsx = d.zsx; g.zoy = d.zoy; g.zox = d.zox;
+    g.chunk_scale = nullptr;
     return g;
 }
 

@@ -227,6 +227,9 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
 
             float accv[HN];
             for (int c = 0; c < nchunks; ++c) {
+                // weight of this chunk in the register-level sum: 1 (fmaf(v, 1, acc) == acc + v exactly), or the per-pixel
+                // blend weight of the chunk's tap (ConvGeom::chunk_scale)
+                const float csc = (g.chunk_scale && valid) ? __ldg(g.chunk_scale + (long long)c * g.OH * g.OW + (long long)y * g.OW + x) : 1.f;
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN);
@@ -235,7 +238,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
                     float v[16];
                     tmem_ld16(taddr + p * 16, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) accv[p * 16 + i] = c == 0 ? v[i] : accv[p * 16 + i] + v[i];
+                    for (int i = 0; i < 16; ++i) accv[p * 16 + i] = c == 0 ? v[i] * csc : fmaf(v[i], csc, accv[p * 16 + i]);
                 }
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[acc]);
@@ -294,7 +297,11 @@ static int launch_bn(const ConvTmaps& maps, const ConvGeom& g, const EpiParams& 
     // two-level accumulation: at most TC_MAX_CHUNK_ITERS (tap, slab) steps are chained inside one TMEM accumulator
     const int kiters = g.ntaps * (g.C / TC_KC);
     const int nchunks = ceil_div(kiters, TC_MAX_CHUNK_ITERS);
-    const int chunk_iters = ceil_div(kiters, nchunks);
+    int chunk_iters = ceil_div(kiters, nchunks);
+    if (g.chunk_scale) {      // one chunk per tap (taps are the outer loop of the K order)
+        chunk_iters = g.C / TC_KC;
+        SHGAN_CHECK(chunk_iters <= TC_MAX_CHUNK_ITERS, "chunk_scale needs C <= 256");
+    }
     conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, g, epi, ti, passes, chunk_iters);
     SHGAN_LAUNCH_CHECK();
     return 0;

@@ -6,14 +6,20 @@
 //   1. shu_rfft2_kernel   one CTA per (n,c) plane: radix-2 shared-memory FFT, two real rows packed into one
 //                         complex transform, columns transformed in place, 1/(R*R) scaling ('forward' norm) and
 //                         the DC-to-centre row shift folded into the store.  -> spec1 [N, 2C, R, R/2+1] (re | im)
-//   2. shu_mix_kernel     per-frequency-bin channel mixing for a tile of 32 bins: conv0 (2C x 2C) + bias + ReLU,
+//   2. channel mixing.  C == 32 (the released model): on the tensor cores -- the spectrum is re-laid as NHWC hi/lo planes
+//                         (x R so that the 'forward'-normalised values sit in fp16's normal range) and the two 1x1
+//                         convolutions run through the tcgen05 igemm (conv_tc.cu) with its fp32-class 3-pass scheme:
+//                         conv0 + bias + ReLU as a 1-tap conv, the heterogeneous filter as a 6-"tap" conv whose taps all
+//                         read the same pixel, use the 6 anchor filters df1[:, o*6+k] as weights and are blended per
+//                         frequency bin by cw[k,bin] in the register-level accumulation (ConvGeom::chunk_scale).
+//                         Any other C: shu_mix_kernel, per-frequency-bin fp32 FMA mixing for a tile of 32 bins: conv0 (2C x 2C) + bias + ReLU,
 //                         then the heterogeneous filter out[o] = sum_k cw[k,bin] * sum_i t[i] * df1[i, o*6+k]
 //                         with all weights resident in shared memory (broadcast 128-bit reads, 4 FMA per LDS).
 //                         -> spec2 [N, 2C, R, R/2+1]
 //   3. shu_irfft2_kernel  one CTA per (n,c,band): crop + Gaussian band mask + un-shift folded into the load,
 //                         inverse column FFTs, Hermitian extension with the DC/Nyquist imaginary parts dropped
 //                         (C2R semantics of pocketfft/cuFFT on non-Hermitian input), two rows per complex FFT.
-#include "common.cuh"
+#include "conv_common.cuh"
 
 namespace shgan {
 
@@ -221,6 +227,61 @@ shu_irfft2_kernel(const float* __restrict__ spec2, const float* __restrict__ gau
     }
 }
 
+// ---- 2b. operand packing for the tensor-core mix (C == 32) -------------------------------------
+// w0 hi/lo [64][64] = conv0.weight [o][i]; w1 hi/lo [6][64][64]: w1[k][o][i] = df1[i][o*6+k]; sc [N*64] = `scale`
+__global__ void __launch_bounds__(256)
+shu_pack_kernel(const float* __restrict__ conv0_w, const float* __restrict__ df1_w, __half* w0_hi, __half* w0_lo, __half* w1_hi,
+                __half* w1_lo, float* sc, int n_sc, float scale) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int i = gid; i < 64 * 64; i += stride) split_f32(__ldg(conv0_w + i), w0_hi[i], w0_lo[i]);
+    for (int i = gid; i < 6 * 64 * 64; i += stride) {
+        const int k = i / 4096, o = (i >> 6) & 63, ii = i & 63;
+        split_f32(__ldg(df1_w + ii * 384 + o * 6 + k), w1_hi[i], w1_lo[i]);
+    }
+    for (int i = gid; i < n_sc; i += stride) sc[i] = scale;
+}
+
+static int shu_mix_tensor(const float* spec1, float* spec2, const float* conv0_w, const float* conv0_b, const float* df1_w,
+                          const float* cw, uint8_t* ws, int N, int R, cudaStream_t stream) {
+    const int Rh = R / 2 + 1;
+    const long long px = (long long)N * R * Rh;
+    // workspace: P1 hi | P1 lo | P2 hi | P2 lo (fp16 [N,R,Rh,64]) | Y fp32 [N,R,Rh,64] | w0 hi/lo | w1 hi/lo | sc [N*64]
+    __half* p1_hi = (__half*)ws;
+    __half* p1_lo = p1_hi + px * 64;
+    __half* p2_hi = p1_lo + px * 64;
+    __half* p2_lo = p2_hi + px * 64;
+    float* y = (float*)(p2_lo + px * 64);
+    __half* w0_hi = (__half*)(y + px * 64);
+    __half* w0_lo = w0_hi + 4096;
+    __half* w1_hi = w0_lo + 4096;
+    __half* w1_lo = w1_hi + 6 * 4096;
+    float* sc = (float*)(w1_lo + 6 * 4096);
+    const float scale = (float)R;      // |X_forward-normalised| <= max|x| <= 256 (lrelu_agc clamp): x R stays below fp16 max
+    shu_pack_kernel<<<32, 256, 0, stream>>>(conv0_w, df1_w, w0_hi, w0_lo, w1_hi, w1_lo, sc, N * 64, scale);
+    SHGAN_LAUNCH_CHECK();
+    if (int e = shgan_nchw_to_planes(spec1, nullptr, nullptr, sc, p1_hi, p1_lo, N, 64, R, Rh, 0, 64, stream)) return e;
+
+    ConvGeom g{};
+    g.num_src = 1; g.src_hi[0] = p1_hi; g.src_lo[0] = p1_lo; g.src_h[0] = R; g.src_w[0] = Rh;
+    g.N = N; g.C = 64; g.Co = 64; g.w_hi = w0_hi; g.w_lo = w0_lo;
+    g.ntaps = 1; g.tap_src[0] = 0; g.tap_dy[0] = 0; g.tap_dx[0] = 0; g.tap_w[0] = 0;
+    g.OH = R; g.OW = Rh; g.mode = 0; g.chunk_scale = nullptr;
+    EpiParams e0{};
+    e0.wgain = 1.f / scale; e0.bias = conv0_b; e0.act = 1; e0.act_alpha = 0.f; e0.act_gain = 1.f; e0.act_clamp = -1.f;   // ReLU
+    e0.next_scale = sc;                                                                                                  // x R again
+    e0.out_hi = p2_hi; e0.out_lo = p2_lo;
+    if (int e = launch_conv_tc(g, e0, 0, 3, stream)) return e;
+
+    g.src_hi[0] = p2_hi; g.src_lo[0] = p2_lo; g.w_hi = w1_hi; g.w_lo = w1_lo;
+    g.ntaps = 6;
+    for (int k = 0; k < 6; ++k) { g.tap_src[k] = 0; g.tap_dy[k] = 0; g.tap_dx[k] = 0; g.tap_w[k] = k; }
+    g.chunk_scale = cw;                 // [6][R*Rh]
+    EpiParams e1{};
+    e1.wgain = 1.f / scale; e1.act = 0; e1.act_gain = 1.f; e1.act_clamp = -1.f; e1.out_f32 = y;
+    if (int e = launch_conv_tc(g, e1, 0, 3, stream)) return e;
+    return shgan_nhwc_to_nchw_f32(y, spec2, N, 64, R, Rh, stream);
+}
+
 static inline int log2_exact(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -232,7 +293,10 @@ static inline int log2_exact(int v) {
 using namespace shgan;
 
 extern "C" int64_t shgan_shu_workspace_bytes(int N, int C, int R) {
-    return 2LL * N * 2 * C * R * (R / 2 + 1) * (int64_t)sizeof(float);
+    const int64_t bins = (int64_t)R * (R / 2 + 1);
+    int64_t b = 2LL * N * 2 * C * bins * (int64_t)sizeof(float);                  // spec1, spec2
+    if (C == 32) b += N * bins * 64 * (4 * 2 + 4) + 2 * 7 * 4096 * 2 + (int64_t)N * 64 * 4 + 256;   // tensor-core mix operands
+    return b;
 }
 
 extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* conv0_b, const float* df1_w, const float* cw,
@@ -262,10 +326,16 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     shu_rfft2_kernel<<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, C, R, log2R);
     SHGAN_LAUNCH_CHECK();
 
-    const size_t mix_smem = ((size_t)K2 * K2 + K2 + (size_t)K2 * K2 * 6 + 2 * (size_t)K2 * MIX_TB) * sizeof(float);
-    dim3 mgrid(ceil_div(bins, MIX_TB), N);
-    shu_mix_kernel<<<mgrid, 256, mix_smem, stream>>>(spec1, conv0_w, conv0_b, df1_w, cw, spec2, K2, bins);
-    SHGAN_LAUNCH_CHECK();
+    if (C == 32) {
+        uint8_t* mix_ws = (uint8_t*)(spec2 + (long long)N * K2 * bins);
+        mix_ws = (uint8_t*)(((uintptr_t)mix_ws + 255) & ~(uintptr_t)255);
+        if (int e = shu_mix_tensor(spec1, spec2, conv0_w, conv0_b, df1_w, cw, mix_ws, N, R, stream)) return e;
+    } else {
+        const size_t mix_smem = ((size_t)K2 * K2 + K2 + (size_t)K2 * K2 * 6 + 2 * (size_t)K2 * MIX_TB) * sizeof(float);
+        dim3 mgrid(ceil_div(bins, MIX_TB), N);
+        shu_mix_kernel<<<mgrid, 256, mix_smem, stream>>>(spec1, conv0_w, conv0_b, df1_w, cw, spec2, K2, bins);
+        SHGAN_LAUNCH_CHECK();
+    }
 
     ShuBands bands;
     bands.num_bands = num_bands;
