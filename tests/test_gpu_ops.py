@@ -253,6 +253,23 @@ def test_shu_golden(golden):
         assert relerr(yb[r].cpu().numpy(), ref[r]) <= 2e-5
 
 
+def test_shu_narrow_uses_fma_mix():
+    """C != 32: the fp32-FMA channel-mix kernel (the tensor-core mix needs 2C == 64) against the oracle."""
+    from shgan_b200.model_zoo.shgan import SHU
+    g = rng(77)
+    c = 16
+    sd = {'s.conv0.weight': (g.standard_normal((2 * c, 2 * c, 1, 1)) / 6).astype(np.float32),
+          's.conv0.bias': (0.1 * g.standard_normal(2 * c)).astype(np.float32),
+          's.df1.weight': (1 / 64 + 0.1 / 64 * g.standard_normal((2 * c, 2 * c * 6))).astype(np.float32)}
+    shu = SHU(c, c, dfilter_freedom=[2, 3], dfilter_type='piecewise_linear', input_res=32, lowest_res=4)
+    shu.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    x = g.standard_normal((2, c, 32, 32)).astype(np.float32)
+    y = shu.to(DEV)(t(x))
+    ref = O.shu_forward(sd, x, prefix='s', input_res=32, lowest_res=4)
+    for r in ref:
+        assert relerr(y[r].cpu().numpy(), ref[r]) <= 2e-5, r
+
+
 def test_fir_decimate_and_mbstd():
     from shgan_b200 import kernels as K
     r = np.random.default_rng(8)
