@@ -9,9 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
-from oracle import shgan_oracle as O  # noqa: E402  (deterministic synthetic weights/inputs only)
-import helpers as H  # noqa: E402
+from shgan_b200 import synthetic as S  # noqa: E402
 
 
 def main():
@@ -24,11 +22,10 @@ def main():
     ap.add_argument('--graphs', type=int, default=1)
     ap.add_argument('--layers', action='store_true', help='per-call timing via launch blocking events')
     a = ap.parse_args()
-    sd = O.synthetic_state_dict(a.res, seed=0)
-    G = H.build_generator(a.res, sd, device='cuda')
+    G = S.random_generator(a.res, seed=0, device='cuda')
     G.engine(passes=a.passes, impl=a.impl, graphs=bool(a.graphs) and not a.layers)
-    x, z = O.synthetic_inputs(a.batch, a.res, seed=0)
-    x, z = torch.from_numpy(x).cuda(), torch.from_numpy(z).cuda()
+    x, z = S.synthetic_batch(a.batch, a.res, seed=0)
+    x, z = x.cuda(), z.cuda()
     for _ in range(2):
         G(x, z, None, noise_mode='random')
     torch.cuda.synchronize()
