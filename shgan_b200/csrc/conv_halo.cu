@@ -21,8 +21,8 @@
 // accumulation (chunks of <= 4 (tap, slab) steps chained in TMEM, drained into fp32 registers with round-to-nearest
 // adds by the epilogue warps while the other TMEM buffer accumulates), the fused epilogue of common.cuh, RAW scatter
 // mode for the transposed-conv parity passes, persistent CTAs over a static tile schedule.
-// Warp roles: warp 0 = weight-slot TMA producer, warp 1 = TMEM allocator + MMA issuer, warp 2 = halo-tile TMA
-// producer, warps 4-11 = epilogue.
+// Warp roles: warp 0 = weight-slot TMA producer, warp 1 = TMEM allocator + MMA issuer of M-block 0, warp 2 = halo-tile TMA
+// producer, warp 3 = MMA issuer of M-block 1, warps 4-11 = epilogue.
 #include "conv_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -135,15 +135,15 @@ conv_halo_kernel(const __grid_constant__ HaloTmaps maps, const ConvGeom g, const
         prefetch_tmap(&maps.w_lo);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], 1);
+            mbar_init(&a_empty[s], HL_NBLK);     // one commit per MMA-issuing thread
         }
         for (int s = 0; s < NACC; ++s) {
-            mbar_init(&t_full[s], 1);
+            mbar_init(&t_full[s], HL_NBLK);
             mbar_init(&t_empty[s], HL_EPI_THREADS);
         }
         for (int s = 0; s < W_SLOTS; ++s) {
             mbar_init(&w_full[s], 1);
-            mbar_init(&w_empty[s], 1);
+            mbar_init(&w_empty[s], HL_NBLK);
         }
         mbar_fence_init();
     }
@@ -207,8 +207,13 @@ conv_halo_kernel(const __grid_constant__ HaloTmaps maps, const ConvGeom g, const
                     }
                 }
             }
-        } else if (warp == 1) {
-            // ===================== MMA issuer =====================
+        } else if (warp == 1 || warp == 3) {
+            // ===================== MMA issuers: warp 1 owns M-block 0, warp 3 owns M-block 1 =====================
+            // Two issuing threads because one thread gets an N <= 128 MMA out only every ~66-80 clocks once the barrier
+            // waits and commits are in its loop; two threads add up to 50 (N = 64) / 65 (N = 128, the tensor floor) clocks
+            // per MMA (tools/mma_rate_probe.cu).  They wait on the same full barriers; every barrier the MMAs release
+            // (w_empty, a_empty, t_full) counts one commit per issuer.
+            const int blk = warp == 1 ? 0 : 1;
             // The issue loop is kept lean: the tensor pipe retires an N = 128 MMA every 64 clocks, and (measured) its issue
             // queue is shallow, so ~60 uniform-datapath instructions of descriptor arithmetic after each barrier wait show
             // up as idle tensor cycles.  Descriptors are therefore formed by ADDING 16-byte-unit offsets to low words
@@ -250,15 +255,12 @@ conv_halo_kernel(const __grid_constant__ HaloTmaps maps, const ConvGeom g, const
                                 tc_fence_after();
                                 uint32_t wb = w_lo0 + (uint32_t)slot * W_SLOT16;
 #pragma unroll
-                                for (int blk = 0; blk < HL_NBLK; ++blk) {
-#pragma unroll
-                                    for (int k = 0; k < HL_KC / 16; ++k) {
-                                        const uint64_t db = ((uint64_t)DESC_HI << 32) | (wb + k * K16);
-                                        umma_f16(d_tmem + blk * BN, ((uint64_t)DESC_HI << 32) | (th + blk * BLK16 + k * K16), db, idesc,
-                                                 (in_chunk | k) != 0);
-                                        if (passes == 3)
-                                            umma_f16(d_tmem + blk * BN, ((uint64_t)DESC_HI << 32) | (tl + blk * BLK16 + k * K16), db, idesc, 1);
-                                    }
+                                for (int k = 0; k < HL_KC / 16; ++k) {
+                                    const uint64_t db = ((uint64_t)DESC_HI << 32) | (wb + k * K16);
+                                    umma_f16(d_tmem + blk * BN, ((uint64_t)DESC_HI << 32) | (th + blk * BLK16 + k * K16), db, idesc,
+                                             (in_chunk | k) != 0);
+                                    if (passes == 3)
+                                        umma_f16(d_tmem + blk * BN, ((uint64_t)DESC_HI << 32) | (tl + blk * BLK16 + k * K16), db, idesc, 1);
                                 }
                                 umma_commit(&w_empty[slot]);
                                 if (++slot == W_SLOTS) { slot = 0; w_phase ^= 1; }
@@ -270,12 +272,9 @@ conv_halo_kernel(const __grid_constant__ HaloTmaps maps, const ConvGeom g, const
                                     tc_fence_after();
                                     wb = w_lo0 + (uint32_t)slot * W_SLOT16;
 #pragma unroll
-                                    for (int blk = 0; blk < HL_NBLK; ++blk) {
-#pragma unroll
-                                        for (int k = 0; k < HL_KC / 16; ++k)
-                                            umma_f16(d_tmem + blk * BN, ((uint64_t)DESC_HI << 32) | (th + blk * BLK16 + k * K16),
-                                                     ((uint64_t)DESC_HI << 32) | (wb + k * K16), idesc, 1);
-                                    }
+                                    for (int k = 0; k < HL_KC / 16; ++k)
+                                        umma_f16(d_tmem + blk * BN, ((uint64_t)DESC_HI << 32) | (th + blk * BLK16 + k * K16),
+                                                 ((uint64_t)DESC_HI << 32) | (wb + k * K16), idesc, 1);
                                     umma_commit(&w_empty[slot]);
                                     if (++slot == W_SLOTS) { slot = 0; w_phase ^= 1; }
                                 }
@@ -292,7 +291,7 @@ conv_halo_kernel(const __grid_constant__ HaloTmaps maps, const ConvGeom g, const
                         }
                     }
                 }
-                HPROF_STORE(0)
+                if (blk == 0) { HPROF_STORE(0) }
             }
         }
     } else {
@@ -461,7 +460,12 @@ double conv_halo_efficiency(const ConvGeom& g) {
 // transposed-convolution passes at 17^2 .. 65^2 (too few tile pairs for the two-SM kernel at 17^2), whose 1-4 tap K loops
 // are too short to amortise the per-tap kernel's per-tile operand latency.
 bool conv_prefers_halo(const ConvGeom& g) {
-    if (g.mode != 1 || g.num_src != 1 || g.C < 512 || g.ntaps < 2) return false;
+    if (g.num_src != 1) return false;
+    // 64 -> 64 channel layers at 256^2 and above (the first encoder / last synthesis convolutions): with two issuing threads the
+    // halo kernel's N = 64 MMAs go out every ~50 clocks and its operand traffic is a third of the per-tap kernel's
+    // (2.04 vs 2.18 ms for the two 512^2 layers at batch 16)
+    if (g.mode == 0 && g.C == 64 && g.Co == 64 && g.ntaps == 9 && g.OW >= 256 && g.OH >= 256) return conv_halo_efficiency(g) >= 0.8;
+    if (g.mode != 1 || g.C < 512 || g.ntaps < 2) return false;
     if (g.OW < 17 || g.OW > 65 || g.OH < 17 || g.OH > 65) return false;
     return conv_halo_efficiency(g) >= 0.6;
 }

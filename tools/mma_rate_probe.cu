@@ -100,6 +100,42 @@ __global__ void probe(long long* out, int iters, int shift, int mode, int conten
         const long long t1 = clock64();
         if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = n_mma; }
         *stop = 1;
+    } else if (warp == 1 && (contend & 256) && N <= 128) {
+        // SECOND issuing thread (another warp), its own accumulators (TMEM columns 256..): do two issuers add up?
+        if (elect_one()) {
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            long long n_mma = 0;
+            const long long t0 = clock64();
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t toff = (uint32_t)((shift * (it & 3) + (it & 7)) * 128);
+                mbar_wait(&bar[6], 0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int blk = 0; blk < 2; ++blk)
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t ao = toff + blk * 16384 + k * 32;
+                        const uint64_t db = desc_sw128(sb_hi + k * 32);
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(tmem + 256 + blk * N), "l"(desc_sw128(sa_hi + ao)), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(tmem + 256 + blk * N), "l"(desc_sw128(sa_lo + ao)), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                    }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[5])) : "memory");
+                mbar_wait(&bar[6], 0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int blk = 0; blk < 2; ++blk)
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t ao = toff + blk * 16384 + k * 32;
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(tmem + 256 + blk * N), "l"(desc_sw128(sa_hi + ao)), "l"(desc_sw128(sb_lo + k * 32)), "r"(idesc), "r"(1u) : "memory");
+                    }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[5])) : "memory");
+                n_mma += 24;
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[4])) : "memory");
+            mbar_wait(&bar[4], 0);
+            const long long t1 = clock64();
+            if (blockIdx.x == 0) { out[4] = t1 - t0; out[5] = n_mma; }
+        }
     } else if (warp >= 4 && (contend & 64)) {
         // 8 warps polling an mbarrier that never completes (what epilogue warps waiting for the MMA do)
         long long n = 0;
@@ -180,12 +216,14 @@ void run(long long* dout, int grid, int shift, int mode, int contend = 0, int co
     const int smem_bytes = 1024 + 2 * 51200 + 2 * 32768 + 32768 + 128;
     cudaFuncSetAttribute(probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     const int iters = mode == 0 ? 4000 : ((contend & 32) ? 40000 : 200);
-    cudaMemset(dout, 0, 32);
+    cudaMemset(dout, 0, 64);
     probe<N><<<grid, 384, smem_bytes>>>(dout, iters, shift, mode, contend, g_src, g_sink, commit_every);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
-    long long h[4];
-    cudaMemcpy(h, dout, 32, cudaMemcpyDeviceToHost);
+    long long h[8];
+    cudaMemcpy(h, dout, 64, cudaMemcpyDeviceToHost);
+    if (h[5]) printf("   two issuers: thread A %.1f clk/MMA, thread B %.1f clk/MMA -> aggregate %.1f clk/MMA\n", (double)h[0] / h[1], (double)h[4] / h[5],
+                     (double)(h[0] > h[4] ? h[0] : h[4]) / (double)(h[1] + h[5]));
     const double cpm = (double)h[0] / (double)h[1];
     printf("N=%3d grid=%3d mode=%d shift=%2d contend=%2d commit_every=%d: %7.1f clk/MMA  (floor %d)  -> %.0f%% of the tensor floor; bulk-copy %.1f B/clk; polls/warp %lld\n", N, grid, mode, shift,
            contend, commit_every, cpm, N / 2, 100.0 * (N / 2) / cpm, (double)h[2] / (double)h[0], h[3]);
@@ -193,14 +231,13 @@ void run(long long* dout, int grid, int shift, int mode, int contend = 0, int co
 
 int main() {
     long long* dout;
-    cudaMalloc(&dout, 32);
+    cudaMalloc(&dout, 64);
     cudaMalloc(&g_src, 148 * 4 * 8192);
     cudaMemset(g_src, 0, 148 * 4 * 8192);
     cudaMalloc(&g_sink, (1024 + 148 * 4096 * 4) * 4);
-    for (int c : {0, 64, 128}) {
+    for (int c : {0, 256}) {
         run<64>(dout, 148, 3, 1, c, 11);
         run<128>(dout, 148, 3, 1, c, 11);
-        run<256>(dout, 148, 3, 1, c, 11);
     }
     return 0;
 }
