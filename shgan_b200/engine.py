@@ -344,11 +344,27 @@ class GeneratorEngine:
             return L['noise_const'], 0
         return torch.randn([n, 1, r, r], device=self.dev, generator=gen), r * r  # stylegan.py:282-283
 
-    def synthesis(self, x_global, feats, ws, noise_mode='random', comp_x=None):
+    def draw_noise(self, n, noise_mode):
+        """The per-layer noise inputs of one synthesis pass, drawn in the reference's layer order (stylegan.py:282-283:
+        b4.conv, then conv0, conv1 of every block), so that a fixed torch seed gives the reference's noise.  Returned as
+        {layer name: (tensor, per-sample stride)}; `_forward_eager` draws them on the side stream while the encoder runs."""
+        out = {}
+        for r in self.syn_res:
+            d = self.syn[r]
+            if r == 4:
+                out['b4.conv'] = self._noise(d['conv'], n, noise_mode)
+            else:
+                out[f'b{r}.conv0'] = self._noise(d['conv0'], n, noise_mode)
+                out[f'b{r}.conv1'] = self._noise(d['conv1'], n, noise_mode)
+        return out
+
+    def synthesis(self, x_global, feats, ws, noise_mode='random', comp_x=None, noise=None):
         """comodgan.Synthesis.forward (comodgan.py:396-433).  Returns img fp32 [N,3,R,R] (+ uint8 composite)."""
         self._ensure()
         n = x_global.shape[0]
         act = self.act
+        if noise is None:
+            noise = self.draw_noise(n, noise_mode)
         st = self.styles(ws, x_global)
         names = [L['name'] for L in self.style_layers]
 
@@ -378,7 +394,7 @@ class GeneratorEngine:
                     for px in range(2):
                         self._conv([x], L0, P.taps_up2(py, px), P.up2_pass_size(h, py), P.up2_pass_size(h, px),
                                    raw=(z, 2, 2, py, px))
-                nz, sn = self._noise(L0, n, noise_mode)
+                nz, sn = noise[name0]
                 y = self._planes(f's{r}.mid', n, r, r, L0['co'])
                 epi = K.make_epilogue(dcoef=st[name0][1], noise=nz, noise_sn=sn, noise_strength=L0['noise_strength'],
                                       bias=L0['bias'], act=act.on, act_alpha=act.alpha, act_gain=act.gain, act_clamp=act.clamp,
@@ -386,7 +402,7 @@ class GeneratorEngine:
                 K.fir_nhwc(z, self.f_applied, 4.0, (1, 1, 1, 1), epi)
                 x = y
                 L, name = d['conv1'], f'b{r}.conv1'
-            nz, sn = self._noise(L, n, noise_mode)
+            nz, sn = noise[name]
             nblk = K.conv_num_nblocks(L['co'])
             part = self._f32(f's{r}.rgb', n, r, r, nblk, 4)
             nxt = next_conv_style(name)
@@ -450,14 +466,19 @@ class GeneratorEngine:
 
     def _forward_eager(self, x, z, noise_mode='random', composite=False):
         self._ensure()
-        with self._fork():                              # the mapping network only meets the encoder at the style affines
-            w = self.mapping(z)
+        with self._fork():                              # the mapping network only meets the encoder at the style affines,
+            w = self.mapping(z)                         # the noise inputs only meet the synthesis layers
+            noise = self.draw_noise(z.shape[0], noise_mode)
+        if self.dev.type == 'cuda' and not torch.cuda.is_current_stream_capturing():
+            for t, _ in noise.values():                 # drawn on the side stream, consumed on this one
+                if t is not None and noise_mode == 'random':
+                    t.record_stream(torch.cuda.current_stream())
         num_ws = self.G.num_ws
         ws = w.unsqueeze(1).expand(w.shape[0], num_ws, w.shape[1])
         x = x.contiguous().float()
         x_global, feats = self.encoder(x)
         self._join()
-        return self.synthesis(x_global, feats, ws, noise_mode=noise_mode, comp_x=x if composite else None)
+        return self.synthesis(x_global, feats, ws, noise_mode=noise_mode, comp_x=x if composite else None, noise=noise)
 
 
 class DiscriminatorEngine:
