@@ -1,6 +1,8 @@
-// tcgen05 tensor-core implementation of shgan_conv_igemm: the convolution hot path of the SH-GAN
-// generator (replaces cuDNN conv / conv_transpose reached from conv2d_resample.py:26-51 and the
-// per-sample weight materialisation of stylegan.py:149-190).
+// Single-CTA, per-tap tcgen05 tensor-core implementation of shgan_conv_igemm (replaces cuDNN conv / conv_transpose
+// reached from conv2d_resample.py:26-51 and the per-sample weight materialisation of stylegan.py:149-190).  Of the
+// three tensor-core kernels behind that entry point (conv_api.cu picks per layer) this one serves the Co = 64
+// transposed-conv passes, the 4x4 .. 16x16 layers (multi-image tiles) and the SHU's channel mix; the two-SM kernel
+// (conv_pair.cu) takes the Co % 128 == 0 layers, the halo kernel (conv_halo.cu) the 64 -> 64 layers at >= 256^2.
 //
 // Im2col-free implicit GEMM, one CTA per SM, persistent over output tiles:
 //   D[128 pixels, BN out-channels] += A_tap[128 pixels, 64 ch] * W_tap[BN, 64 ch]^T   for every tap and 64-ch slab
@@ -21,9 +23,11 @@
 // * Two-level accumulation.  The tensor core truncates (does not round) when it adds into the fp32 TMEM
 //   accumulator, which shows up as a bias that grows linearly with the number of chained MMAs (measured:
 //   2.5e-6 relative after 108 MMAs, 1.5e-5 after 864).  The K loop is therefore cut into chunks of at most
-//   4 (tap, slab) steps; each chunk accumulates in one of the two TMEM accumulators (2*BN columns) while the
-//   epilogue warps drain the other one and add it into fp32 registers with round-to-nearest FADDs.  This
+//   4 (tap, slab) steps; each chunk accumulates in one of the 512 / BN TMEM accumulator buffers while the
+//   epilogue warps drain a finished one and add it into fp32 registers with round-to-nearest FMAs.  This
 //   bounds the truncation chain for every layer width and is also what overlaps epilogue and MMA.
+// * The per-(sample, channel) epilogue vectors are staged in shared memory per tile for BN < 256 (conv_common.cuh),
+//   plane outputs leave through 256-bit stores, and producer / issuer loops run under elect.sync (tc_ptx.cuh).
 #include "conv_common.cuh"
 #include "tc_ptx.cuh"
 
