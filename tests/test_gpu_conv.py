@@ -85,6 +85,7 @@ def test_igemm_tc_single_pass_and_block_n():
     assert 1e-5 < relerr(y1, ref) <= 3e-3
     for bn in (64, 128):
         assert relerr(_igemm_plain(x, wt, 3, block_n=bn), ref) <= 3e-6
+    assert 1e-5 < relerr(_igemm_plain(x, wt, 4, passes=1), ref) <= 3e-3     # two-SM kernel, single pass
 
 
 @pytest.mark.parametrize('impl', IMPLS)
