@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SHGAN_B200_ABI_VERSION 2
+#define SHGAN_B200_ABI_VERSION 3
 #define SHGAN_MAX_TAPS 16
 #define SHGAN_MAX_SRC 4
 
@@ -159,6 +159,14 @@ int shgan_fromrgb(const float* x, const float* w /*[Co,Ci]*/, const float* bias,
 int shgan_torgb_combine(const float* img_prev, const float* rgb_partial, int n_blocks, const float* bias,
                         const float* f /*[4,4]*/, float* img_out, int N, int H, int W,
                         const float* comp_x /*[N,4,H,W] or NULL*/, uint8_t* comp_out, void* stream);
+
+/* eval-loop input preparation: x[n,0] = mask - 0.5 ; x[n,1+j] = real[n,j] * mask   (all NCHW fp32; real [N,3,H,W], mask
+ * [N,1,H,W] in {0,1}, x [N,4,H,W]).  replaces the sub / mul / torch.cat of lib/experiments/shgan_default.py:269-274. */
+int shgan_prepare_input(const float* real, const float* mask, float* x, int N, int H, int W, void* stream);
+/* out[n,0] = x[n,0] ; out[n,1+j] = x[n,1+j]*m + img[n,j]*(1-m), m = x[n,0] + 0.5: the float composite of
+ * lib/experiments/shgan_default.py:257-260 concatenated with the mask channel = the discriminator's input of the
+ * generator+discriminator step (BASELINE.json config C4).  x, out [N,4,H,W]; img [N,3,H,W]; NCHW fp32. */
+int shgan_composite_cat(const float* x, const float* img, float* out, int N, int H, int W, void* stream);
 
 /* minibatch_std_layer (num_channels = 1) fused with the channel concat of lib/model_zoo/stylegan.py:686-705:
  * out planes [N,H,W,C_out] = [ in planes [N,H,W,C] | std statistic of the sample's group | zeros ]. */

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libshgan_b200.so')
 
 SHGAN_MAX_TAPS = 16
 SHGAN_MAX_SRC = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 vp = C.c_void_p
 fp = C.c_void_p  # float* passed as raw device addresses
@@ -72,6 +72,8 @@ SIGNATURES = {
     'shgan_fir_nhwc': (i32, [fp, vp, vp, fp, i32, i32, f32] + [i32] * 8 + [C.POINTER(Epilogue), i32, vp]),
     'shgan_fromrgb': (i32, [fp, fp, fp, f32, f32, f32, f32, vp, vp] + [i32] * 5 + [vp]),
     'shgan_torgb_combine': (i32, [fp, fp, i32, fp, fp, fp, i32, i32, i32, fp, vp, vp]),
+    'shgan_prepare_input': (i32, [fp, fp, fp, i32, i32, i32, vp]),
+    'shgan_composite_cat': (i32, [fp, fp, fp, i32, i32, i32, vp]),
     'shgan_mbstd_append': (i32, [vp, vp, vp, vp] + [i32] * 6 + [vp]),
     'shgan_dense_fwd': (i32, [fp, i64, i32, fp, i64, fp, fp, fp, i64, i32, i32, i32, f32, f32, i32, f32, f32, f32, vp]),
     'shgan_normalize_2nd_moment': (i32, [fp, fp, i32, i32, vp]),

@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/shgan_b200.h"
@@ -40,6 +41,30 @@ extern std::atomic<uint64_t> g_launch_count;
         ::shgan::g_launch_count.fetch_add(1, std::memory_order_relaxed);                \
         SHGAN_CUDA(cudaGetLastError());                                                 \
     } while (0)
+
+// One-time per-DEVICE initialisation of a kernel family (cudaFuncSetAttribute is a per-device setting, and one process may
+// drive several GPUs): runs `set_attrs` the first time the calling thread's current device is seen, under a mutex, and
+// returns that device's SM count in *num_sms.
+constexpr int SHGAN_MAX_DEVICES = 64;
+struct DeviceInit {
+    std::mutex mu;
+    int sms[SHGAN_MAX_DEVICES] = {0};      // 0 = this device has not been initialised yet
+};
+template <class F>
+static inline int device_init(DeviceInit& st, int* num_sms, F&& set_attrs) {
+    int dev = 0;
+    SHGAN_CUDA(cudaGetDevice(&dev));
+    SHGAN_CHECK(dev >= 0 && dev < SHGAN_MAX_DEVICES, "device ordinal out of range");
+    std::lock_guard<std::mutex> lock(st.mu);
+    if (!st.sms[dev]) {
+        if (int e = set_attrs()) return e;
+        int n = 0;
+        SHGAN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        st.sms[dev] = n;
+    }
+    if (num_sms) *num_sms = st.sms[dev];
+    return 0;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

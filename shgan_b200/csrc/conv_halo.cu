@@ -474,15 +474,12 @@ template <int BN>
 static int launch_halo_bn(const HaloTmaps& maps, const ConvGeom& g, const EpiParams& epi, const HaloTile& ti, int passes,
                           cudaStream_t stream) {
     using Cfg = HaloCfg<BN>;
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
-        SHGAN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_MAX));
-        int dev = 0;
-        SHGAN_CUDA(cudaGetDevice(&dev));
-        SHGAN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
+    static DeviceInit once;
+    int num_sms = 0;
+    if (int e = device_init(once, &num_sms, []() -> int {
+            SHGAN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_MAX));
+            return 0;
+        })) return e;
     const int smem_bytes = 4 * ti.a_px * 128 + Cfg::FIXED_BYTES;
     SHGAN_CHECK(smem_bytes <= HL_SMEM_MAX, "halo tile does not fit in shared memory");
     const int grid = ti.total < num_sms ? ti.total : num_sms;

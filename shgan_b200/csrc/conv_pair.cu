@@ -375,15 +375,12 @@ bool conv_prefers_pair(const ConvGeom& g) {
 template <int BN>
 static int launch_pair_bn(const PairTmaps& maps, const ConvGeom& g, const EpiParams& epi, const PairTile& ti, int passes, cudaStream_t stream) {
     using Cfg = PairCfg<BN>;
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
-        SHGAN_CUDA(cudaFuncSetAttribute(conv_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        int dev = 0;
-        SHGAN_CUDA(cudaGetDevice(&dev));
-        SHGAN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
+    static DeviceInit once;
+    int num_sms = 0;
+    if (int e = device_init(once, &num_sms, []() -> int {
+            SHGAN_CUDA(cudaFuncSetAttribute(conv_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+            return 0;
+        })) return e;
     const int max_clusters = num_sms / 2;
     const int clusters = ti.total_pairs < max_clusters ? ti.total_pairs : max_clusters;
     const int kiters = g.ntaps * (g.C / CP_KC);

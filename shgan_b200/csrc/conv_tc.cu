@@ -288,15 +288,12 @@ template <int BN>
 static int launch_bn(const ConvTmaps& maps, const ConvGeom& g, const EpiParams& epi, const TileInfo& ti, int passes,
                      cudaStream_t stream) {
     using Cfg = TcCfg<BN>;
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
-        SHGAN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        int dev = 0;
-        SHGAN_CUDA(cudaGetDevice(&dev));
-        SHGAN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
+    static DeviceInit once;
+    int num_sms = 0;
+    if (int e = device_init(once, &num_sms, []() -> int {
+            SHGAN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+            return 0;
+        })) return e;
     const int grid = ti.total < num_sms ? ti.total : num_sms;
     // two-level accumulation: at most TC_MAX_CHUNK_ITERS (tap, slab) steps are chained inside one TMEM accumulator
     const int kiters = g.ntaps * (g.C / TC_KC);
@@ -355,7 +352,7 @@ int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int pas
     }
     int w_taps = 0;
     for (int t = 0; t < g.ntaps; ++t) w_taps = g.tap_w[t] + 1 > w_taps ? g.tap_w[t] + 1 : w_taps;
-    // the caller-declared w_taps bounds the map; use the larger of the two so a bad tap index cannot read past it
+    // the weight map covers exactly the taps this launch references (tap_w < w_taps was validated by shgan_conv_igemm)
     const uint64_t wdims[2] = {(uint64_t)g.C, (uint64_t)w_taps * g.Co};
     const uint32_t wbox[2] = {(uint32_t)TC_KC, (uint32_t)block_n};
     if (int e = encode_map(&maps.w_hi, g.w_hi, 2, wdims, wbox)) return e;

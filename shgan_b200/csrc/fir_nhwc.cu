@@ -527,16 +527,13 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
     SHGAN_CHECK((long long)N * C * ((long long)OH + 1) * (OW + 1) <= INT32_MAX, "tensor is too large");
     if (N == 0) return 0;
     EpiParams epi = make_epi(*epi_);
-    static bool attr_set = false;
-    static int num_sms = 148;
-    if (!attr_set) {
-        SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
-        SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
-        int dev = 0;
-        SHGAN_CUDA(cudaGetDevice(&dev));
-        SHGAN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
-    }
+    static DeviceInit once;
+    int num_sms = 148;
+    if (int e = device_init(once, &num_sms, []() -> int {
+            SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+            SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
+            return 0;
+        })) return e;
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)IW, (uint64_t)IH, (uint64_t)N};
     int skip_rank1 = 0;
     // measured on B200, batch 16, 64 channels @512^2: planes input (encoder down path) 0.78 ms two-phase vs 0.91 ms TMA-staged

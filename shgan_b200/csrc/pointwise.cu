@@ -172,9 +172,76 @@ mbstd_append_kernel(const __half* __restrict__ in_hi, const __half* __restrict__
     }
 }
 
+// eval-loop input preparation (lib/experiments/shgan_default.py:269-274): x = cat([mask - 0.5, real * mask])
+__global__ void __launch_bounds__(256)
+prepare_input_kernel(const float* __restrict__ real, const float* __restrict__ mask, float* __restrict__ x, long long total4, int hw4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / hw4;
+        const int p = (int)(i - n * hw4);
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mask) + i);
+        float4* xo = reinterpret_cast<float4*>(x) + n * 4 * hw4 + p;
+        xo[0] = make_float4(m.x - 0.5f, m.y - 0.5f, m.z - 0.5f, m.w - 0.5f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(real) + (n * 3 + j) * hw4 + p);
+            xo[(long long)(1 + j) * hw4] = make_float4(r.x * m.x, r.y * m.y, r.z * m.z, r.w * m.w);
+        }
+    }
+}
+
+// float composite of the eval loop (shgan_default.py:257-260) concatenated with the mask channel: the discriminator's input
+__global__ void __launch_bounds__(256)
+composite_cat_kernel(const float* __restrict__ x, const float* __restrict__ img, float* __restrict__ out, long long total4, int hw4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / hw4;
+        const int p = (int)(i - n * hw4);
+        const float4* xi = reinterpret_cast<const float4*>(x) + n * 4 * hw4 + p;
+        float4* o = reinterpret_cast<float4*>(out) + n * 4 * hw4 + p;
+        const float4 c0 = __ldg(xi);
+        o[0] = c0;
+        const float4 m = make_float4(__fadd_rn(c0.x, 0.5f), __fadd_rn(c0.y, 0.5f), __fadd_rn(c0.z, 0.5f), __fadd_rn(c0.w, 0.5f));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 a = __ldg(xi + (long long)(1 + j) * hw4);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(img) + (n * 3 + j) * hw4 + p);
+            // x*m + img*(1-m) with the reference's operation order and no contraction into FMAs
+            o[(long long)(1 + j) * hw4] = make_float4(__fadd_rn(__fmul_rn(a.x, m.x), __fmul_rn(g.x, __fsub_rn(1.f, m.x))),
+                                                      __fadd_rn(__fmul_rn(a.y, m.y), __fmul_rn(g.y, __fsub_rn(1.f, m.y))),
+                                                      __fadd_rn(__fmul_rn(a.z, m.z), __fmul_rn(g.z, __fsub_rn(1.f, m.z))),
+                                                      __fadd_rn(__fmul_rn(a.w, m.w), __fmul_rn(g.w, __fsub_rn(1.f, m.w))));
+        }
+    }
+}
+
 }  // namespace shgan
 
 using namespace shgan;
+
+extern "C" int shgan_prepare_input(const float* real, const float* mask, float* x, int N, int H, int W, void* stream) {
+    SHGAN_CHECK(real && mask && x, "null pointer");
+    SHGAN_CHECK(N >= 0 && H >= 1 && W >= 1 && ((long long)H * W) % 4 == 0, "H*W must be a multiple of 4");
+    if (N == 0) return 0;
+    const int hw4 = (int)((long long)H * W / 4);
+    const long long total4 = (long long)N * hw4;
+    long long blocks = ceil_div64(total4, 256);
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    prepare_input_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(real, mask, x, total4, hw4);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shgan_composite_cat(const float* x, const float* img, float* out, int N, int H, int W, void* stream) {
+    SHGAN_CHECK(x && img && out, "null pointer");
+    SHGAN_CHECK(N >= 0 && H >= 1 && W >= 1 && ((long long)H * W) % 4 == 0, "H*W must be a multiple of 4");
+    if (N == 0) return 0;
+    const int hw4 = (int)((long long)H * W / 4);
+    const long long total4 = (long long)N * hw4;
+    long long blocks = ceil_div64(total4, 256);
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    composite_cat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, img, out, total4, hw4);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int shgan_mbstd_append(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int N, int H, int W, int C,
                                   int C_out, int group_size, void* stream) {

@@ -315,13 +315,13 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     float* spec1 = (float*)spec_ws;
     float* spec2 = spec1 + (long long)N * K2 * bins;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        SHGAN_CUDA(cudaFuncSetAttribute(shu_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        SHGAN_CUDA(cudaFuncSetAttribute(shu_irfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        SHGAN_CUDA(cudaFuncSetAttribute(shu_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
+    static DeviceInit once;
+    if (int e = device_init(once, nullptr, []() -> int {
+            SHGAN_CUDA(cudaFuncSetAttribute(shu_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            SHGAN_CUDA(cudaFuncSetAttribute(shu_irfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            SHGAN_CUDA(cudaFuncSetAttribute(shu_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            return 0;
+        })) return e;
     const size_t fft_smem_bytes = ((size_t)(R / 2) * R + (size_t)R * Rh + R / 2) * sizeof(float2);
     shu_rfft2_kernel<<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, C, R, log2R);
     SHGAN_LAUNCH_CHECK();

@@ -14,6 +14,7 @@ Per-layer mapping of reference ops to launches:
   synthesis conv1 / b4.conv : 1 x shgan_conv_igemm (demod, noise, bias, lrelu, fused torgb, next-layer style)
   torgb + img upsample      : shgan_torgb_combine
 """
+import functools
 import gc
 import math
 
@@ -29,6 +30,23 @@ SQRT2 = math.sqrt(2.0)
 def _check_device(dev):
     if dev.type != 'cuda':
         raise RuntimeError('shgan_b200 runs on CUDA devices only (no CPU fallback): move the generator to cuda')
+
+
+def _on_engine_device(fn):
+    """Runs an engine entry point with the parameters' device as the current CUDA device, so that streams, graph capture,
+    RNG state and every kernel launch go to the GPU that owns the model even when the caller never called
+    torch.cuda.set_device (the reference eval does not: lib/experiments/shgan_default.py:164)."""
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        self._ensure()
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.device != self.dev:
+                raise RuntimeError(f'{type(self).__name__}.{fn.__name__}: input on {a.device}, parameters on {self.dev}')
+        if self.dev.type != 'cuda' or torch.cuda.current_device() == self.dev.index:    # (CPU: host-logic tests only)
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.dev):
+            return fn(self, *args, **kwargs)
+    return wrapped
 
 
 class _Act:
@@ -68,6 +86,8 @@ class GeneratorEngine:
         enc, syn = G.encoder, G.synthesis
         dev = next(G.parameters()).device
         _check_device(dev)
+        if dev.type == 'cuda' and dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
         self.dev = dev
         self.res = syn.resolution
         self.act = _Act(syn.activation)
@@ -234,6 +254,7 @@ class GeneratorEngine:
         w, b, wg, bg, act = spec
         return K.dense(x0, w, b, out, wg, bg, act.on, act.alpha, act.gain, act.clamp, x1=x1)
 
+    @_on_engine_device
     def mapping(self, z):
         """Mapping.forward (stylegan.py:394-430) for c_dim == 0, truncation_psi == 1 -> w [N, w_dim]."""
         self._ensure()
@@ -251,6 +272,7 @@ class GeneratorEngine:
         return K.make_epilogue(wgain=L['wgain'], bias=L['bias'], act=a.on, act_alpha=a.alpha, act_gain=a.gain,
                                act_clamp=a.clamp, out=out)
 
+    @_on_engine_device
     def encoder(self, x):
         """shgan.Encoder.forward (shgan.py:361-383) -> (x_global fp32 [N,oc_n], feats {res: Planes})."""
         self._ensure()
@@ -358,6 +380,7 @@ class GeneratorEngine:
                 out[f'b{r}.conv1'] = self._noise(d['conv1'], n, noise_mode)
         return out
 
+    @_on_engine_device
     def synthesis(self, x_global, feats, ws, noise_mode='random', comp_x=None, noise=None):
         """comodgan.Synthesis.forward (comodgan.py:396-433).  Returns img fp32 [N,3,R,R] (+ uint8 composite)."""
         self._ensure()
@@ -423,6 +446,7 @@ class GeneratorEngine:
         self._join()
         return (img, comp) if comp_x is not None else img
 
+    @_on_engine_device
     def forward(self, x, z, noise_mode='random', composite=False):
         """comodgan.Generator.forward (comodgan.py:449-481).  composite=True additionally returns the eval loop's
         uint8 composite (shgan_default.py:257-262) fused into the last kernel.  With `graphs` the launch sequence is
@@ -436,14 +460,14 @@ class GeneratorEngine:
         if entry is None:
             xs = x.detach().contiguous().float().clone()
             zs = z.detach().contiguous().float().clone()
-            cur = torch.cuda.current_stream()
-            side = torch.cuda.Stream()
+            cur = torch.cuda.current_stream(self.dev)
+            side = torch.cuda.Stream(device=self.dev)
             side.wait_stream(cur)
             rng = torch.cuda.get_rng_state(self.dev)
             with torch.cuda.stream(side):      # warm-up: allocates the persistent buffers, loads the kernels
                 self._forward_eager(xs, zs, noise_mode, composite)
             cur.wait_stream(side)
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(self.dev)
             torch.cuda.set_rng_state(rng, self.dev)   # the warm-up must not consume the caller's random stream
             graph = torch.cuda.CUDAGraph()
             # no cyclic garbage collection while the stream is capturing: collecting an unreachable generator/engine of an
@@ -464,6 +488,7 @@ class GeneratorEngine:
         graph.replay()
         return out
 
+    @_on_engine_device
     def _forward_eager(self, x, z, noise_mode='random', composite=False):
         self._ensure()
         with self._fork():                              # the mapping network only meets the encoder at the style affines,
@@ -498,6 +523,8 @@ class DiscriminatorEngine:
         D = self.D
         dev = next(D.parameters()).device
         _check_device(dev)
+        if dev.type == 'cuda' and dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
         self.dev = dev
         self.act = _Act(D.activation)
         self.res_list = list(D.encode_res)
@@ -546,10 +573,13 @@ class DiscriminatorEngine:
                                    act_clamp=a.clamp * gain if a.clamp > 0 else -1.0, skip=skip, out=out)
         return K.make_epilogue(wgain=L['wgain'], bias=L['bias'], act=False, act_gain=gain, skip=skip, out=out)
 
-    def forward(self, img):
+    def _ensure(self):
         if self._sig is None or self._sig != self._signature():
             self.refresh()
             self._buf = {}
+
+    @_on_engine_device
+    def forward(self, img):
         img = img.contiguous().float()
         n = img.shape[0]
         g = math.sqrt(0.5)

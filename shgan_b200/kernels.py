@@ -5,6 +5,7 @@ device pointers plus the current torch stream to the library, and returns the ca
 Nothing here computes on the CPU and there is no fallback implementation.
 """
 import ctypes as C
+import functools
 import math
 
 import torch
@@ -16,7 +17,41 @@ SQRT2 = math.sqrt(2.0)
 
 
 def _stream():
+    # called inside `_on_tensor_device`, so the current device is the tensors' device
     return torch.cuda.current_stream().cuda_stream
+
+
+def _find_devices(obj, found):
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            found.add(obj.device.index)
+    elif isinstance(obj, Planes):
+        _find_devices(obj.hi, found)
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            _find_devices(o, found)
+    elif isinstance(obj, dict):
+        for o in obj.values():
+            _find_devices(o, found)
+
+
+def _on_tensor_device(fn):
+    """Every launch goes to the device that owns the tensors, on that device's current torch stream -- not to whatever
+    device happens to be current (the reference eval puts rank r's model on cuda:r without torch.cuda.set_device,
+    lib/experiments/shgan_default.py:164; its own op runs under an OptionalCUDAGuard, upfirdn2d.cpp:31).  Tensors on
+    two different devices in one call are an error."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        found = set()
+        _find_devices(args, found)
+        _find_devices(kwargs, found)
+        if len(found) > 1:
+            raise RuntimeError(f'{fn.__name__}: tensors live on different CUDA devices {sorted(found)}')
+        if not found or next(iter(found)) == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(next(iter(found))):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def _p(t):
@@ -69,6 +104,7 @@ def make_epilogue(dcoef=None, wgain=1.0, noise=None, noise_sn=0, noise_strength=
 
 
 # ---- upfirdn2d -----------------------------------------------------------------------------------
+@_on_tensor_device
 def upfirdn2d_fwd(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
     """Same contract as the reference pybind op (upfirdn2d.cpp:16): allocates and returns y."""
     _f32c(x, 'x'); _f32c(f, 'f')
@@ -87,6 +123,7 @@ def upfirdn2d_fwd(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip
 
 
 # ---- layout ----------------------------------------------------------------------------------------
+@_on_tensor_device
 def nchw_to_planes(x, add=None, scale=None, out=None, c_off=0):
     _f32c(x, 'x')
     n, c, h, w = x.shape
@@ -100,6 +137,7 @@ def nchw_to_planes(x, add=None, scale=None, out=None, c_off=0):
     return out
 
 
+@_on_tensor_device
 def planes_to_nchw(p, c_off=0, c=None, out=None):
     n, h, w, c_tot = p.shape
     c = c_tot - c_off if c is None else c
@@ -111,6 +149,7 @@ def planes_to_nchw(p, c_off=0, c=None, out=None):
     return out
 
 
+@_on_tensor_device
 def planes_add_nchw(p, x, c_off):
     _f32c(x, 'x')
     n, c, h, w = x.shape
@@ -120,6 +159,7 @@ def planes_add_nchw(p, x, c_off):
     return p
 
 
+@_on_tensor_device
 def nhwc_to_nchw_f32(x):
     _f32c(x, 'x')
     n, h, w, c = x.shape
@@ -130,6 +170,7 @@ def nhwc_to_nchw_f32(x):
 
 
 # ---- convolution -------------------------------------------------------------------------------------
+@_on_tensor_device
 def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0):
     """srcs: list of Planes [N,Hs,Ws,C]; w_hi/w_lo: fp16 [w_taps, Co, C]; taps: list of (src, dy, dx, w_tap).
     epi: Epilogue (ACT mode)  or  raw = (z fp32 [N,ZH,ZW,Co], zsy, zsx, zoy, zox) (RAW mode)."""
@@ -161,6 +202,7 @@ def conv_num_nblocks(co, block_n=0):
     return _lib.load().shgan_conv_num_nblocks(co, block_n)
 
 
+@_on_tensor_device
 def fir_nhwc(src, f, gain, pads, epi, parity_split=False):
     """src: Planes or fp32 NHWC tensor; pads = (pad_x0, pad_x1, pad_y0, pad_y1); f: fp32 [4,4] (as applied)."""
     lib = _lib.load()
@@ -177,6 +219,7 @@ def fir_nhwc(src, f, gain, pads, epi, parity_split=False):
 
 
 # ---- pointwise ---------------------------------------------------------------------------------------
+@_on_tensor_device
 def fromrgb(x, w, bias, wgain, act_alpha, act_gain, act_clamp, out):
     _f32c(x, 'x')
     n, ci, h, wd = x.shape
@@ -186,6 +229,7 @@ def fromrgb(x, w, bias, wgain, act_alpha, act_gain, act_clamp, out):
     return out
 
 
+@_on_tensor_device
 def torgb_combine(img_prev, rgb_partial, bias, f, img_out, comp_x=None, comp_out=None):
     n, _, h, w = img_out.shape
     lib = _lib.load()
@@ -194,6 +238,31 @@ def torgb_combine(img_prev, rgb_partial, bias, f, img_out, comp_x=None, comp_out
     return img_out
 
 
+@_on_tensor_device
+def prepare_input(real, mask, out=None):
+    """x = cat([mask - 0.5, real * mask]) (shgan_default.py:269-274).  real [N,3,H,W], mask [N,1,H,W] or [N,H,W]."""
+    _f32c(real, 'real'); _f32c(mask, 'mask')
+    n, _, h, w = real.shape
+    if out is None:
+        out = torch.empty((n, 4, h, w), dtype=torch.float32, device=real.device)
+    lib = _lib.load()
+    _lib.check(lib.shgan_prepare_input(_p(real), _p(mask), _p(out), n, h, w, _stream()), 'shgan_prepare_input')
+    return out
+
+
+@_on_tensor_device
+def composite_cat(x, img, out=None):
+    """cat([x[:, 0:1], x[:, 1:4]*m + img*(1-m)]), m = x[:, 0:1] + 0.5 (shgan_default.py:257-260): the discriminator input."""
+    _f32c(x, 'x'); _f32c(img, 'img')
+    n, _, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, 4, h, w), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.shgan_composite_cat(_p(x), _p(img), _p(out), n, h, w, _stream()), 'shgan_composite_cat')
+    return out
+
+
+@_on_tensor_device
 def mbstd_append(src, out, group_size):
     n, h, w, c = src.shape
     lib = _lib.load()
@@ -203,6 +272,7 @@ def mbstd_append(src, out, group_size):
 
 
 # ---- dense / styles ------------------------------------------------------------------------------------
+@_on_tensor_device
 def dense(x0, w, bias, out, wgain, bgain=1.0, act=False, act_alpha=0.2, act_gain=SQRT2, act_clamp=256.0, x1=None):
     """out[b,o] = act((cat[x0,x1][b] . w[o]) * wgain + bias[o]*bgain).  x0/x1/out may be strided row views."""
     b, i0 = x0.shape
@@ -216,6 +286,7 @@ def dense(x0, w, bias, out, wgain, bgain=1.0, act=False, act_alpha=0.2, act_gain
     return out
 
 
+@_on_tensor_device
 def normalize_2nd_moment(z, out=None):
     _f32c(z, 'z')
     out = torch.empty_like(z) if out is None else out
@@ -225,6 +296,7 @@ def normalize_2nd_moment(z, out=None):
     return out
 
 
+@_on_tensor_device
 def style_prep(styles, wsq, s_hat, dcoef, demod, pre_scale=1.0):
     n, ci = styles.shape
     co = dcoef.shape[1] if dcoef is not None else 1
@@ -233,6 +305,7 @@ def style_prep(styles, wsq, s_hat, dcoef, demod, pre_scale=1.0):
                                    _stream()), 'shgan_style_prep')
 
 
+@_on_tensor_device
 def style_prep_batched(raw, layers):
     """raw fp32 [N, S] (row stride raw.stride(0)); layers: list of dicts(offset, ci, co, demod, pre_scale, wsq, s_hat, dcoef)."""
     tb = _lib.StyleBatch()
@@ -249,6 +322,7 @@ def shu_workspace_bytes(n, c, r):
     return int(_lib.load().shgan_shu_workspace_bytes(n, c, r))
 
 
+@_on_tensor_device
 def shu_fwd(x, conv0_w, conv0_b, df1_w, cw, gauss, outs, lowest_res, workspace=None):
     """x fp32 [N,C,R,R]; outs: list of fp32 [N,C,r,r] for r = lowest_res*2^k; gauss: concatenated band masks."""
     _f32c(x, 'x')

@@ -71,22 +71,47 @@ class EvalLoop:
 
     def __init__(self, G, detector, batch_size, device, z_seed=0):
         self.G, self.detector, self.batch_size, self.device = G, detector, batch_size, device
-        self.gen = torch.Generator(device='cpu').manual_seed(z_seed)
+        self.z_seed = int(z_seed)
+
+    def latent(self, index):
+        """z of dataset item `index`: a function of (z_seed, index) only, so every item gets its own latent whatever the
+        rank count and the sharding (the reference seeds per rank, rnd_seed*gpu_count+RANK, lib/experiments/
+        shgan_default.py:160-166: independent across ranks, but world-size dependent)."""
+        g = torch.Generator(device='cpu').manual_seed((self.z_seed << 32) + int(index))
+        return torch.randn([self.G.z_dim], generator=g)
+
+    def prepare(self, real, mask):
+        """x = cat([mask - 0.5, real * mask]) (shgan_default.py:269-274): one kernel on the GPU; plain torch ops only in the
+        CPU tests of the host logic."""
+        if real.is_cuda:
+            from . import kernels as K
+            return K.prepare_input(real.contiguous().float(), mask.contiguous().float())
+        return torch.cat([mask - 0.5, real * mask], dim=1)
 
     def run(self, dataset, n_items, noise_mode='random'):
+        """-> (fake [n_items, D], real [n_items, D]) float64 detector features in dataset order, on every rank.
+        ONE all_gather for the whole run: fake features, real features and the item index travel as one
+        [n_local, 2D+1] matrix; the gathered index column must come back as 0..n_items-1 (checked on the device)."""
         rank = dist.get_rank() if dist.is_initialized() else 0
         world = dist.get_world_size() if dist.is_initialized() else 1
         mine = shard_indices(n_items, rank, world)
-        feats_fake, feats_real = [], []
+        rows = []
         for b0 in range(0, len(mine), self.batch_size):
-            items = [dataset(i) for i in mine[b0:b0 + self.batch_size]]
+            idx = mine[b0:b0 + self.batch_size]
+            items = [dataset(i) for i in idx]
             real = torch.stack([it[0] for it in items]).to(self.device, non_blocking=True)
             mask = torch.stack([it[1] for it in items])[:, None].to(self.device, non_blocking=True)
-            x = torch.cat([mask - 0.5, real * mask], dim=1)                       # shgan_default.py:271-274
-            z = torch.randn([x.shape[0], self.G.z_dim], generator=self.gen).to(self.device)
+            x = self.prepare(real, mask)
+            z = torch.stack([self.latent(i) for i in idx]).to(self.device, non_blocking=True)
             _, fake_u8 = self.G.forward_composite(x, z, noise_mode=noise_mode)
-            feats_fake.append(self.detector(fake_u8).to(torch.float64))
-            feats_real.append(self.detector((real * 127.5 + 127.5).clamp(0, 255).to(torch.uint8)).to(torch.float64))
-        fake = gather_features(torch.cat(feats_fake), n_items)
-        real = gather_features(torch.cat(feats_real), n_items)
-        return fake, real
+            f_fake = self.detector(fake_u8).to(torch.float64)
+            f_real = self.detector((real * 127.5 + 127.5).clamp(0, 255).to(torch.uint8)).to(torch.float64)
+            col = torch.tensor(idx, dtype=torch.float64, device=f_fake.device)[:, None]
+            rows.append(torch.cat([f_fake, f_real, col], dim=1))
+        full = gather_features(torch.cat(rows), n_items)
+        self.last_gather_bytes = int(world * len(mine) * full.shape[1] * 8)
+        d = (full.shape[1] - 1) // 2
+        order_ok = torch.equal(full[:, -1], torch.arange(n_items, dtype=torch.float64, device=full.device))
+        if not order_ok:
+            raise RuntimeError('feature gather returned items out of dataset order')
+        return full[:, :d], full[:, d:2 * d]

@@ -10,38 +10,76 @@ import torch
 ACT = 'lrelu_agc(alpha=0.2, gain=sqrt_2, clamp=256)'
 
 
-def freeform_mask(res, rng, hole_range=(0.0, 1.0)):
-    """Free-form mask in the spirit of RandomMask / RandomBrush (lib/data_factory/ds_ffhq.py:145-217): random thick
-    poly-line strokes plus random rectangles, re-drawn until the hole ratio falls in `hole_range`.  1 = keep."""
-    s = res
-    for _ in range(50):
-        m = np.ones((s, s), np.float32)
-        for _ in range(int(rng.integers(1, 5))):      # rectangles
-            w, h = int(rng.integers(s // 8, s // 2)), int(rng.integers(s // 8, s // 2))
-            x0, y0 = int(rng.integers(0, s - w)), int(rng.integers(0, s - h))
-            m[y0:y0 + h, x0:x0 + w] = 0
-        for _ in range(int(rng.integers(1, 4))):      # brush strokes
-            px, py = float(rng.integers(0, s)), float(rng.integers(0, s))
-            width = int(rng.integers(max(2, s // 40), max(3, s // 10)))
-            for _ in range(int(rng.integers(2, 8))):
-                ang, ln = rng.uniform(0, 2 * math.pi), rng.uniform(s / 16, s / 3)
-                qx = float(np.clip(px + ln * math.cos(ang), 0, s - 1))
-                qy = float(np.clip(py + ln * math.sin(ang), 0, s - 1))
-                for t in np.linspace(0, 1, int(max(abs(qx - px), abs(qy - py))) + 1):
-                    cx, cy = int(px + (qx - px) * t), int(py + (qy - py) * t)
-                    m[max(cy - width // 2, 0):cy + width // 2 + 1, max(cx - width // 2, 0):cx + width // 2 + 1] = 0
-                px, py = qx, qy
-        hole = 1.0 - float(m.mean())
-        if hole_range[0] <= hole <= hole_range[1]:
-            return m
-    return m
+def _brush_strokes(rs, max_tries, s, vertex_range=(4, 18), mean_angle=2 * math.pi / 5, angle_range=2 * math.pi / 15,
+                   width_range=(12, 48)):
+    """`RandomBrush` (lib/data_factory/ds_ffhq.py:145-196) restated on an explicit legacy RandomState: poly-line strokes
+    with round joints, drawn with PIL like the reference (the rasteriser is part of the result).  The draw ORDER of the
+    random numbers is the reference's, so RandomState(seed) reproduces np.random.seed(seed) bit for bit.  Returns a
+    uint8 [s,s] array, 1 = brushed (hole)."""
+    from PIL import Image, ImageDraw
+    mean_radius = math.hypot(s, s) / 8
+    canvas = Image.new('L', (s, s), 0)
+    for _ in range(rs.randint(max_tries)):
+        n_vertex = rs.randint(*vertex_range)
+        lo = mean_angle - rs.uniform(0, angle_range)
+        hi = mean_angle + rs.uniform(0, angle_range)
+        turns = [(2 * math.pi - rs.uniform(lo, hi)) if k % 2 == 0 else rs.uniform(lo, hi) for k in range(n_vertex)]
+        side_a, side_b = canvas.size
+        pts = [(int(rs.randint(0, side_b)), int(rs.randint(0, side_a)))]
+        for ang in turns:
+            step = np.clip(rs.normal(loc=mean_radius, scale=mean_radius // 2), 0, 2 * mean_radius)
+            px = np.clip(pts[-1][0] + step * math.cos(ang), 0, side_b)
+            py = np.clip(pts[-1][1] + step * math.sin(ang), 0, side_a)
+            pts.append((int(px), int(py)))
+        pen = ImageDraw.Draw(canvas)
+        width = int(rs.uniform(*width_range))
+        pen.line(pts, fill=1, width=width)
+        for vx, vy in pts:
+            pen.ellipse((vx - width // 2, vy - width // 2, vx + width // 2, vy + width // 2), fill=1)
+        rs.random_sample()        # the reference draws two coins here whose transposes are discarded (ds_ffhq.py:185-188)
+        rs.random_sample()
+    out = np.asarray(canvas, np.uint8)
+    if rs.random_sample() > 0.5:
+        out = np.flip(out, 0)
+    if rs.random_sample() > 0.5:
+        out = np.flip(out, 1)
+    return out
+
+
+def random_mask(s, rs, hole_range=(0.0, 1.0)):
+    """`RandomMask(s, hole_range)` (lib/data_factory/ds_ffhq.py:198-217): random rectangles (up to 10*coef of side < s/2,
+    up to 5*coef of side < s) AND-ed with the complement of the brush strokes; re-drawn until the hole ratio lies strictly
+    inside `hole_range`.  rs: np.random.RandomState (RandomState(k) == the reference under np.random.seed(k)).
+    Returns float32 [1,s,s], 1 = keep."""
+    coef = min(hole_range[0] + hole_range[1], 1.0)
+    while True:
+        keep = np.ones((s, s), np.uint8)
+        for tries, max_size in ((int(10 * coef), s // 2), (int(5 * coef), s)):
+            for _ in range(rs.randint(tries)):
+                w, h = rs.randint(max_size), rs.randint(max_size)
+                x = rs.randint(-(w // 2), s - w + w // 2)
+                y = rs.randint(-(h // 2), s - h + h // 2)
+                keep[max(y, 0):min(y + h, s), max(x, 0):min(x + w, s)] = 0
+        keep = np.logical_and(keep, 1 - _brush_strokes(rs, int(20 * coef), s))
+        hole = 1 - np.mean(keep)
+        if hole_range is not None and (hole <= hole_range[0] or hole >= hole_range[1]):
+            continue
+        return keep[np.newaxis].astype(np.float32)
+
+
+def freeform_mask(res, rng=None, hole_range=(0.0, 1.0)):
+    """Free-form mask [res,res] float32 (1 = keep) = the reference's RandomMask; `rng` is a np.random.RandomState (or an
+    int seed)."""
+    rs = rng if isinstance(rng, np.random.RandomState) else np.random.RandomState(0 if rng is None else int(rng))
+    return random_mask(res, rs, hole_range)[0]
 
 
 def synthetic_batch(batch, res, seed=0, z_dim=512):
     """-> (x [B,4,R,R] float32, z [B,z_dim] float32) CPU tensors."""
     rng = np.random.default_rng(seed)
     img = np.clip(rng.standard_normal((batch, 3, res, res)), -1, 1).astype(np.float32)
-    mask = np.stack([freeform_mask(res, rng) for _ in range(batch)])[:, None]
+    rs = np.random.RandomState(seed)             # masks: RandomMask(res, [0, 1]) as under np.random.seed(seed)
+    mask = np.stack([freeform_mask(res, rs) for _ in range(batch)])[:, None]
     x = np.concatenate([mask - 0.5, img * mask], axis=1).astype(np.float32)
     z = rng.standard_normal((batch, z_dim)).astype(np.float32)
     return torch.from_numpy(x), torch.from_numpy(z)

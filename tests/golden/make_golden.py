@@ -231,22 +231,7 @@ def gen_shu(R):
     save('shu', **out)
 
 
-def build_reference_generator(R, resolution, ch_base=32768, ch_max=512, num_ws=None):
-    log2 = int(np.log2(resolution))
-    if num_ws is None:
-        num_ws = {256: 14, 512: 16, 1024: 18}.get(resolution, 2 * log2 - 2)
-    m = R.comodgan.Mapping(z_dim=512, c_dim=0, w_dim=512, num_ws=num_ws, num_layers=8, embed_features=None,
-                           layer_features=None, activation=ACT, lr_multiplier=0.01, w_avg_beta=0.995)
-    e = R.shgan.Encoder(resolution=resolution, ic_n=4, oc_n=1024, ch_base=ch_base, ch_max=ch_max, use_fp16_before_res=None,
-                        resample_filter=[1, 3, 3, 1], activation=ACT, mbstd_group_size=0, mbstd_c_n=0, c_dim=None,
-                        cmap_dim=None, use_dropout=True, has_extra_final_layer=False, shu_channels=32, shu_df_freedom=[2, 3],
-                        shu_df_type='piecewise_linear', shu_input_res=64, shu_lowest_res=4, shu_tail_sigma_mult=3,
-                        shu_gaussian_at_input_res=False)
-    s = R.comodgan.Synthesis(w_dim=512, w0_dim=1024, resolution=resolution, rgb_n=3, ch_base=ch_base, ch_max=ch_max,
-                             use_fp16_after_res=None, resample_filter=[1, 3, 3, 1], activation=ACT)
-    if not hasattr(s, 'num_ws'):
-        s.num_ws = num_ws  # comodgan.py:362-367 only defines it for 256/512/1024
-    return R.comodgan.Generator(m, e, s).eval().requires_grad_(False)
+build_reference_generator = ref_import.build_reference_generator
 
 
 GENERATOR_CASES = [
@@ -317,6 +302,79 @@ def gen_discriminator(R):
         save(name, out=y, x4=inter[4], x8=inter[8])
 
 
+# The configurations bench.py actually times (BASELINE.json configs C2 / C3): the batch changes the tile schedule
+# (multi-image tiles, the odd last tile pair of the two-SM kernel) and the batch-global style normaliser
+# (stylegan.py:147), so they get their own fixtures.  A [B,3,R,R] fp32 image set is 50 MB at C3: the fixture keeps a
+# strided sub-sample whose phase differs per sample (sample n keeps pixels (n%4 + 4i, (n//4)%4 + 4j), so the 16 phases of
+# the 4x4 lattice are all covered) plus per-sample statistics of the full images.
+BENCH_CASES = [
+    # name, resolution, batch, seed
+    ('gen512_b16', 512, 16, 14),
+    ('gen256_b32', 256, 32, 15),
+]
+BENCH_STRIDE = 4
+
+
+def bench_subsample(img):
+    st = BENCH_STRIDE
+    return np.stack([img[n, :, (n % st)::st, ((n // st) % st)::st] for n in range(img.shape[0])])
+
+
+def gen_bench_configs(R, only=None):
+    for name, res, batch, seed in BENCH_CASES:
+        if only and only != name:
+            continue
+        sd = O.synthetic_state_dict(res, seed=seed)
+        G = build_reference_generator(R, res)
+        G.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+        x, z = O.synthetic_inputs(batch, res, seed=seed)
+        torch.set_num_threads(os.cpu_count() or 1)
+        imgs = []
+        with torch.no_grad():
+            # ONE call over the whole batch: the style normaliser is batch-global
+            img = G(t(x), t(z), torch.zeros(batch, 0), noise_mode='const').numpy()
+        xt, it = t(x), t(img)
+        u8 = (xt[:, 1:4] * (xt[:, 0:1] + 0.5) + it * (1 - (xt[:, 0:1] + 0.5)))
+        u8 = (u8 * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).numpy()
+        stats = np.stack([[v.mean(), v.std(), np.abs(v).max(), np.abs(v).astype(np.float64).sum()] for v in img]).astype(np.float64)
+        print(f'  {name}: |img|max {np.abs(img).max():.3f}')
+        save(name, img_sub=bench_subsample(img), composite_sub=bench_subsample(u8), stats=stats)
+
+
+def gen_discriminator512(R):
+    name, res, batch, seed = 'disc512', 512, 8, 23
+    sd = O.synthetic_discriminator_state_dict(res, seed=seed)
+    D = ref_import.build_reference_discriminator(R, res)
+    D.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+    x, _ = O.synthetic_inputs(batch, res, seed=seed)
+    with torch.no_grad():
+        y = D(t(x), None).numpy()
+    print(f'  {name}: out {y.ravel()[:4]}')
+    save(name, out=y)
+
+
+MASK_CASES = [(0, 512, (0.0, 1.0)), (1, 256, (0.0, 1.0)), (2, 512, (0.2, 0.6))]      # np.random seed, size, hole_range
+
+
+def gen_random_mask():
+    """RandomMask / RandomBrush (lib/data_factory/ds_ffhq.py:145-217) run from the reference source under
+    np.random.seed(seed): 3 consecutive masks per case, bit-packed.  (The two functions are exec'd out of the file because
+    importing lib.data_factory pulls in packages this image does not have.)"""
+    import math
+    from PIL import Image, ImageDraw
+    src = open(os.path.join(ref_import.reference_root(), 'lib', 'data_factory', 'ds_ffhq.py')).read()
+    ns = dict(math=math, np=np, Image=Image, ImageDraw=ImageDraw)
+    exec(src[src.index('def RandomBrush('):src.index('###############\n# ffhq_simple')], ns)
+    out = {}
+    for seed, size, hr in MASK_CASES:
+        np.random.seed(seed)
+        for k in range(3):
+            m = ns['RandomMask'](size, list(hr))
+            out[f'seed{seed}_s{size}_{k}'] = np.packbits(m[0].astype(np.uint8))
+            print(f'  mask seed {seed} size {size} #{k}: hole ratio {1 - m.mean():.3f}')
+    save('random_mask', **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', default=None)
@@ -332,9 +390,18 @@ def main():
     if args.only in (None, 'discriminator'):
         print('discriminator')
         gen_discriminator(R)
-    if args.only is None or args.only.startswith('gen'):
+    if args.only in (None, 'random_mask'):
+        print('random_mask')
+        gen_random_mask()
+    if args.only in (None, 'disc512'):
+        print('discriminator 512')
+        gen_discriminator512(R)
+    if args.only is None or (args.only.startswith('gen') and not args.only.endswith(('_b16', '_b32'))):
         print('generator')
         gen_generator(R, None if args.only in (None, 'generator') else args.only)
+    if args.only in (None, 'bench') or (args.only or '').endswith(('_b16', '_b32')):
+        print('benchmark configurations')
+        gen_bench_configs(R, None if args.only in (None, 'bench') else args.only)
 
 
 if __name__ == '__main__':

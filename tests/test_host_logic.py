@@ -187,3 +187,19 @@ def test_no_cpu_fallback():
                 src += open(os.path.join(root, fn)).read()
     assert 'oracle' not in src.replace('oracle/', '').lower().replace('the oracle', '').replace('cpu oracle', '') or True
     assert 'import oracle' not in src and 'from oracle' not in src
+
+
+def test_random_mask_matches_reference_fixture(golden):
+    """synthetic.random_mask restates RandomMask/RandomBrush (ds_ffhq.py:145-217): bit-identical to the reference under
+    the same np.random seed (fixtures written by tests/golden/make_golden.py from the reference source)."""
+    from shgan_b200 import synthetic as S
+    from golden.make_golden import MASK_CASES
+    g = golden('random_mask')
+    for seed, size, hr in MASK_CASES:
+        rs = np.random.RandomState(seed)
+        for k in range(3):
+            m = S.random_mask(size, rs, hr)
+            assert m.shape == (1, size, size) and m.dtype == np.float32
+            assert np.array_equal(np.packbits(m[0].astype(np.uint8)), g[f'seed{seed}_s{size}_{k}']), (seed, size, k)
+            hole = 1 - m.mean()
+            assert hr[0] < hole < hr[1]
