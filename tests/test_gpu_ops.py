@@ -288,3 +288,17 @@ def test_fir_decimate_and_mbstd():
     got = K.planes_to_nchw(ob).cpu().numpy()
     refb = O.minibatch_std(xb, 4, 1)
     assert relerr(got[:, :65], refb) <= 3e-6 and np.abs(got[:, 65:]).max() == 0
+
+
+def test_prepare_input_and_composite_cat():
+    """The two eval-loop glue kernels against the reference expressions (shgan_default.py:269-274 and :257-260)."""
+    from shgan_b200 import kernels as K
+    g = torch.Generator().manual_seed(9)
+    real = (torch.rand(3, 3, 64, 48, generator=g) * 2 - 1).to(DEV)
+    mask = (torch.rand(3, 1, 64, 48, generator=g) > 0.4).float().to(DEV)
+    x = K.prepare_input(real, mask)
+    assert torch.equal(x, torch.cat([mask - 0.5, real * mask], dim=1))
+    img = torch.randn(3, 3, 64, 48, generator=g).to(DEV) * 3
+    m = x[:, 0:1] + 0.5
+    ref = torch.cat([x[:, 0:1], x[:, 1:4] * m + img * (1 - m)], dim=1)
+    assert torch.equal(K.composite_cat(x, img), ref)
