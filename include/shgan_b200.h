@@ -126,7 +126,13 @@ typedef struct {
                                         cross-check of the tensor-core kernels at full layer sizes (tests);
                                     2 / 3 = force the per-tap / the halo-tile tensor-core kernel (tests, profiling);
                                     4 = the two-SM (cta_group::2) kernel wherever Co % 256 == 0, per-tap elsewhere */
+    float acc_comp;              /* compensation of the tensor core's TRUNCATING fp32 accumulate (measured on B200: every
+                                    chained tcgen05.mma loses ~half an ulp of the running sum towards zero, a relative
+                                    shrink of 1.6e-8 .. 1.8e-8 per chained MMA, tools/acc_bias_probe.py): each chunk of L chained MMAs is scaled by
+                                    (1 + acc_comp * L) when it is drained into the fp32 register sum.
+                                    0 = library default (SHGAN_ACC_COMP_DEFAULT), < 0 = off, > 0 = this value */
 } shgan_conv_desc;
+#define SHGAN_ACC_COMP_DEFAULT 1.6e-8f
 int shgan_conv_igemm(const shgan_conv_desc* d, void* stream);
 /* size of the rgb partial axis: Co / 32 (independent of block_n, kept in the signature for ABI stability) */
 int shgan_conv_num_nblocks(int Co, int block_n);

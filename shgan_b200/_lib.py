@@ -39,7 +39,7 @@ class ConvDesc(C.Structure):
         ('tap_src', i32 * SHGAN_MAX_TAPS), ('tap_dy', i32 * SHGAN_MAX_TAPS), ('tap_dx', i32 * SHGAN_MAX_TAPS),
         ('tap_w', i32 * SHGAN_MAX_TAPS),
         ('OH', i32), ('OW', i32), ('mode', i32), ('z', fp), ('ZH', i32), ('ZW', i32), ('zsy', i32), ('zsx', i32),
-        ('zoy', i32), ('zox', i32), ('epi', Epilogue), ('block_n', i32), ('passes', i32), ('impl', i32),
+        ('zoy', i32), ('zox', i32), ('epi', Epilogue), ('block_n', i32), ('passes', i32), ('impl', i32), ('acc_comp', f32),
     ]
 
 

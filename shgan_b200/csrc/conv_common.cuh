@@ -23,6 +23,8 @@ struct ConvGeom {
     // acc[n,y,x,o] = sum_t chunk_scale[t, y*OW + x] * (tap t's contribution).  Used by the SHU's heterogeneous filter
     // (shu.cu), whose blend over 6 anchor filters is exactly that.  NULL: plain sum.
     const float* chunk_scale;
+    // relative compensation per chained MMA of the truncating tensor-core accumulate (shgan_conv_desc::acc_comp, resolved)
+    float acc_comp;
 };
 
 static inline ConvGeom make_geom(const shgan_conv_desc& d) {
@@ -40,6 +42,7 @@ static inline ConvGeom make_geom(const shgan_conv_desc& d) {
     g.OH = d.OH; g.OW = d.OW; g.mode = d.mode; g.z = d.z; g.ZH = d.ZH; g.ZW = d.ZW;
     g.zsy = d.zsy; g.zsx = d.zsx; g.zoy = d.zoy; g.zox = d.zox;
     g.chunk_scale = nullptr;
+    g.acc_comp = d.acc_comp == 0.f ? SHGAN_ACC_COMP_DEFAULT : (d.acc_comp < 0.f ? 0.f : d.acc_comp);
     return g;
 }
 

@@ -351,6 +351,9 @@ conv_halo_kernel(const __grid_constant__ HaloTmaps maps, const ConvGeom g, const
                 HPROF_BEGIN
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * HL_NBLK * BN + half * HN);
+                // compensation of the truncating accumulate for this chunk's chain of MMAs (ConvGeom::acc_comp)
+                const int n_it = kiters - c * chunk_iters < chunk_iters ? kiters - c * chunk_iters : chunk_iters;
+                const float comp = 1.f + g.acc_comp * (float)(n_it * (passes == 3 ? 12 : 4));
 #pragma unroll
                 for (int blk = 0; blk < HL_NBLK; ++blk) {
 #pragma unroll
@@ -358,7 +361,7 @@ conv_halo_kernel(const __grid_constant__ HaloTmaps maps, const ConvGeom g, const
                         float v[16];
                         tmem_ld16(taddr + blk * BN + p * 16, v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) accv[blk][p * 16 + i] = c == 0 ? v[i] : accv[blk][p * 16 + i] + v[i];
+                        for (int i = 0; i < 16; ++i) accv[blk][p * 16 + i] = c == 0 ? v[i] * comp : fmaf(v[i], comp, accv[blk][p * 16 + i]);
                     }
                 }
                 tc_fence_before();

@@ -305,12 +305,15 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
                 PPROF_BEGIN
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CP_BN + half * HN);
+                // compensation of the truncating accumulate for this chunk's chain of MMAs (ConvGeom::acc_comp)
+                const int n_it = kiters - c * chunk_iters < chunk_iters ? kiters - c * chunk_iters : chunk_iters;
+                const float comp = 1.f + g.acc_comp * (float)(n_it * (passes == 3 ? 12 : 4));
 #pragma unroll
                 for (int p = 0; p < HN / 16; ++p) {
                     float v[16];
                     tmem_ld16(taddr + p * 16, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) accv[p * 16 + i] = c == 0 ? v[i] : accv[p * 16 + i] + v[i];
+                    for (int i = 0; i < 16; ++i) accv[p * 16 + i] = c == 0 ? v[i] * comp : fmaf(v[i], comp, accv[p * 16 + i]);
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -233,7 +233,10 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
             for (int c = 0; c < nchunks; ++c) {
                 // weight of this chunk in the register-level sum: 1 (fmaf(v, 1, acc) == acc + v exactly), or the per-pixel
                 // blend weight of the chunk's tap (ConvGeom::chunk_scale)
-                const float csc = (g.chunk_scale && valid) ? __ldg(g.chunk_scale + (long long)c * g.OH * g.OW + (long long)y * g.OW + x) : 1.f;
+                // times the compensation of the truncating accumulate for this chunk's chain of MMAs (ConvGeom::acc_comp)
+                const int n_it = kiters - c * chunk_iters < chunk_iters ? kiters - c * chunk_iters : chunk_iters;
+                const float csc = ((g.chunk_scale && valid) ? __ldg(g.chunk_scale + (long long)c * g.OH * g.OW + (long long)y * g.OW + x) : 1.f) *
+                                  (1.f + g.acc_comp * (float)(n_it * (passes == 3 ? 12 : 4)));
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN);

@@ -265,7 +265,7 @@ static int shu_mix_tensor(const float* spec1, float* spec2, const float* conv0_w
     g.num_src = 1; g.src_hi[0] = p1_hi; g.src_lo[0] = p1_lo; g.src_h[0] = R; g.src_w[0] = Rh;
     g.N = N; g.C = 64; g.Co = 64; g.w_hi = w0_hi; g.w_lo = w0_lo;
     g.ntaps = 1; g.tap_src[0] = 0; g.tap_dy[0] = 0; g.tap_dx[0] = 0; g.tap_w[0] = 0;
-    g.OH = R; g.OW = Rh; g.mode = 0; g.chunk_scale = nullptr;
+    g.OH = R; g.OW = Rh; g.mode = 0; g.chunk_scale = nullptr; g.acc_comp = SHGAN_ACC_COMP_DEFAULT;
     EpiParams e0{};
     e0.wgain = 1.f / scale; e0.bias = conv0_b; e0.act = 1; e0.act_alpha = 0.f; e0.act_gain = 1.f; e0.act_clamp = -1.f;   // ReLU
     e0.next_scale = sc;                                                                                                  // x R again

@@ -7,6 +7,7 @@ Nothing here computes on the CPU and there is no fallback implementation.
 import ctypes as C
 import functools
 import math
+import os
 
 import torch
 
@@ -14,6 +15,7 @@ from . import _lib
 from ._lib import ConvDesc, Epilogue
 
 SQRT2 = math.sqrt(2.0)
+ACC_COMP = float(os.environ.get('SHGAN_ACC_COMP', '0'))   # development override of shgan_conv_desc::acc_comp
 
 
 def _stream():
@@ -171,7 +173,7 @@ def nhwc_to_nchw_f32(x):
 
 # ---- convolution -------------------------------------------------------------------------------------
 @_on_tensor_device
-def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0):
+def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0, acc_comp=None):
     """srcs: list of Planes [N,Hs,Ws,C]; w_hi/w_lo: fp16 [w_taps, Co, C]; taps: list of (src, dy, dx, w_tap).
     epi: Epilogue (ACT mode)  or  raw = (z fp32 [N,ZH,ZW,Co], zsy, zsx, zoy, zox) (RAW mode)."""
     d = ConvDesc()
@@ -194,6 +196,7 @@ def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, pa
         d.mode = 0
         d.epi = epi
     d.block_n = block_n; d.passes = passes; d.impl = impl
+    d.acc_comp = ACC_COMP if acc_comp is None else acc_comp    # 0 = library default, < 0 = off (include/shgan_b200.h)
     lib = _lib.load()
     _lib.check(lib.shgan_conv_igemm(C.byref(d), _stream()), 'shgan_conv_igemm')
 

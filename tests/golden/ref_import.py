@@ -67,6 +67,11 @@ def import_reference():
     # without a writable home still works, and so that a prebuilt plugin travels with the snapshot
     os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(_REPO, 'baseline', '_ref', 'torch_extensions'))
     os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0')
+    # custom_ops.get_plugin builds with torch.utils.cpp_extension.load and then calls importlib.import_module(name)
+    # (custom_ops.py:111); torch >= 2 no longer leaves the build directory on sys.path, so put it there
+    plug_dir = os.path.join(os.environ['TORCH_EXTENSIONS_DIR'], 'upfirdn2d_plugin')
+    if plug_dir not in sys.path:
+        sys.path.append(plug_dir)
     import lib.model_zoo.stylegan as ref_stylegan
     import lib.model_zoo.comodgan as ref_comodgan
     import lib.model_zoo.shgan as ref_shgan
