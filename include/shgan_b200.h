@@ -137,6 +137,31 @@ int shgan_conv_igemm(const shgan_conv_desc* d, void* stream);
 /* size of the rgb partial axis: Co / 32 (independent of block_n, kept in the signature for ABI stability) */
 int shgan_conv_num_nblocks(int Co, int block_n);
 
+/* ---- up-sampling (stride-2 transposed) 3x3 convolution + 4x4 blur + pointwise epilogue, one launch --------------
+ * replaces: the `up == 2` path of conv2d_resample (lib/model_zoo/stylegan_utils/conv2d_resample.py:123-142:
+ *           conv_transpose2d stride 2 with the un-flipped weights -> upfirdn2d(f, pad 1, gain up^2)) as reached from
+ *           modulated_conv2d (lib/model_zoo/stylegan.py:187-190), and every elementwise pass after it
+ *           (stylegan.py:191-193,298-303; the `+ feats[res]` of comodgan.py:319-320).
+ * z[n, 2i+ky, 2j+kx, o] += sum_c src[n,i,j,c] * w[ky*3+kx, o, c]          (z is never materialised)
+ * out[n,y,x,o] = gain * sum_{a,b<4} fy[a]*fx[b] * z[n, y+a-1, x+b-1, o]   (z = 0 outside [0,2H] x [0,2W]),  y < 2H, x < 2W
+ * then `epi` as documented on shgan_epilogue (no torgb terms).  The blur must be separable (fy (x) fx, as applied, i.e.
+ * already flipped by the caller); src are split planes [N,H,W,C]; weights are packed per block of 64 output channels in
+ * the order the kernel's stacked-N MMAs consume them:
+ *   w_hi/w_lo fp16 [Co/64][9][64][C], slot s holding tap (ky*3+kx) = {3,0,1,4,5,2,6,7,8}[s].   C, Co multiples of 64. */
+typedef struct {
+    const void* src_hi;
+    const void* src_lo;
+    int N, H, W, C, Co;
+    const void* w_hi;
+    const void* w_lo;
+    float fx[4], fy[4];
+    float gain;
+    shgan_epilogue epi;
+    int passes;                  /* 3 (default when 0) or 1, as in shgan_conv_desc */
+    float acc_comp;              /* as in shgan_conv_desc */
+} shgan_up2_desc;
+int shgan_conv_up2(const shgan_up2_desc* d, void* stream);
+
 /* ---- FIR (blur) on NHWC data with the fused pointwise epilogue ---------------------------
  * replaces: upfirdn2d blur passes around resampled convs, conv2d_resample.py:117-120 (down path,
  * pad 2) and :139 (up path, pad 1, gain 4), fused with everything that follows the blur.

@@ -43,6 +43,15 @@ class ConvDesc(C.Structure):
     ]
 
 
+class Up2Desc(C.Structure):
+    """shgan_up2_desc (include/shgan_b200.h)."""
+    _fields_ = [
+        ('src_hi', vp), ('src_lo', vp), ('N', i32), ('H', i32), ('W', i32), ('C', i32), ('Co', i32),
+        ('w_hi', vp), ('w_lo', vp), ('fx', f32 * 4), ('fy', f32 * 4), ('gain', f32), ('epi', Epilogue),
+        ('passes', i32), ('acc_comp', f32),
+    ]
+
+
 SHGAN_MAX_STYLE_LAYERS = 40
 
 
@@ -69,6 +78,7 @@ SIGNATURES = {
     'shgan_nhwc_to_nchw_f32': (i32, [fp, fp] + [i32] * 4 + [vp]),
     'shgan_conv_igemm': (i32, [C.POINTER(ConvDesc), vp]),
     'shgan_conv_num_nblocks': (i32, [i32, i32]),
+    'shgan_conv_up2': (i32, [C.POINTER(Up2Desc), vp]),
     'shgan_fir_nhwc': (i32, [fp, vp, vp, fp, i32, i32, f32] + [i32] * 8 + [C.POINTER(Epilogue), i32, vp]),
     'shgan_fromrgb': (i32, [fp, fp, fp, f32, f32, f32, f32, vp, vp] + [i32] * 5 + [vp]),
     'shgan_torgb_combine': (i32, [fp, fp, i32, fp, fp, fp, i32, i32, i32, fp, vp, vp]),

@@ -1,0 +1,451 @@
+// shgan_conv_up2: the up-sampling modulated convolution of the synthesis network in ONE launch --
+//   conv_transpose2d(stride 2, 3x3, un-flipped weights) -> 4x4 blur (pad 1, gain 4) -> demod, noise, bias, lrelu,
+//   + feats[res] skip, next-layer style, hi/lo split
+// (replaces conv2d_resample.py:123-142 + stylegan.py:187-193,298-303 + comodgan.py:319-320; before: four RAW parity
+// launches of shgan_conv_igemm that wrote the fp32 (2h+1)^2 intermediate `z` to HBM plus one shgan_fir_nhwc launch that
+// read it back).
+//
+// The transposed convolution runs at its algorithmic cost on the INPUT grid.  z[2i+py, 2j+px] (parity (py,px)) only
+// receives the taps ky = py, kx = px (mod 2), read at x[i - (ky>>1), j - (kx>>1)]: 4 + 2 + 2 + 1 = 9 taps over four
+// operand shifts (0,0) (0,-1) (-1,0) (-1,-1).  One CTA tile is 128 flattened positions of a haloed input tile (8 rows x
+// 16 columns, pitch 16, staged ONCE per 64-channel slab by one TMA box; shifted A views are UMMA descriptor start
+// offsets, cf. conv_halo.cu) and its accumulator holds all four parities side by side in TMEM:
+//     columns   0.. 63  parity (1,0)      64..127  parity (0,0)      128..191  parity (0,1)      192..255  parity (1,1)
+// so that every shift is ONE tcgen05.mma per k-step whose B operand stacks the taps of the parities it feeds along N:
+//     shift ( 0, 0): N = 256 at column   0  taps [3,0,1,4]        shift ( 0,-1): N = 128 at column  0  taps [5,2]
+//     shift (-1, 0): N = 128 at column  64  taps [6,7]            shift (-1,-1): N =  64 at column 64  tap  [8]
+// (the N = 64 half-rate MMA shape carries 1/9 of the work instead of all of it).  Weights are pre-packed in exactly that
+// row order (packing.pack_up2_weight).  Precision scheme as everywhere: fp16 hi/lo operands, hi*hi + lo*hi + hi*lo, one
+// 64-channel slab (<= 48 chained MMAs per column) per TMEM chunk, chunks summed in fp32 registers with the truncation
+// compensation (shgan_conv_desc::acc_comp).
+//
+// Epilogue: the 8 epilogue warps drain the chunks (thread = tile position x two parity blocks), then, in two rounds of
+// 32 channels, scatter their parities into a shared-memory z tile [16 z-rows][2 column parities][16][32 ch] (float4 slots
+// XOR-swizzled by the column so that both the position-major writes and the channel-major reads are conflict free),
+// and 208 of the 256 threads run the separable 4-tap blur over it (thread = 4 channels x 2 output columns x 6 output
+// rows, sliding window in registers) followed by the pointwise epilogue, storing 64 contiguous bytes per pixel and plane.
+// A tile owns 12 x 26 outputs and recomputes a 3-row / 3-column z halo (the 15th input column is the wrap-around column
+// of the flattened tile): 61 % of the tensor rows are useful, in exchange for never writing z.
+//
+// Warp roles: warp 0 = weight TMA producer, warp 1 = TMEM allocator + MMA issuer, warp 2 = halo-tile TMA producer,
+// warps 4-11 = epilogue.
+#include "conv_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace shgan {
+
+struct Up2Tmaps {
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+};
+
+struct Up2Params {
+    int N, H, W, C, Co;          // input planes [N,H,W,C]; output [N,2H,2W,Co]
+    int OH, OW;
+    int tiles_x, tiles_y, nblk, total;
+    float fx[4], fy[4];          // separable blur taps as applied (correlation order); gain folded into fy
+    float acc_comp;
+    int passes;
+    // per shift group (issue order), read by the single-thread producer / issuer loops from the constant bank:
+    // instruction descriptor, TMEM column offset, A start offset and weight region offset in 16-byte descriptor units,
+    // number of 64-row weight units and the first unit
+    uint32_t sg_idesc[4], sg_col[4], sg_aoff16[4], sg_wb16[4];
+    int sg_units[4], sg_ubase[4];
+};
+
+constexpr int U2_THREADS = 384;
+constexpr int U2_EPI_THREADS = 256;
+constexpr int U2_REGS_DEC = 56, U2_REGS_INC = 224;
+constexpr int U2_KC = 64;
+constexpr int U2_P = 16;                         // tile pitch (input columns per flattened row)
+constexpr int U2_ROWS = 8;                       // input rows per tile: U2_ROWS * U2_P = 128 = UMMA M
+constexpr int U2_OWN_Y = 12, U2_OWN_X = 26;      // outputs owned by a tile
+constexpr int U2_STEP_I = 6, U2_STEP_J = 13;     // tile step on the input grid
+constexpr int U2_A_BOX_ROWS = (U2_ROWS + 1) * U2_P;          // 144 positions delivered by the TMA box
+constexpr int U2_A_PX = 152;                     // allocated positions per plane (reads reach position 127 + 17)
+constexpr int U2_A_PLANE = U2_A_PX * 128;        // 19456 B, a multiple of 1024
+constexpr int U2_W_UNIT = 64 * 128;              // one [64 co x 64 ci] fp16 block
+constexpr int U2_W_BYTES = 9 * U2_W_UNIT;        // one plane of one slab: 72 KB
+constexpr int U2_ZT_BYTES = 16 * 2 * 16 * 32 * 4;    // 64 KB
+constexpr int U2_BAR_BYTES = 256;
+constexpr int U2_STG_BYTES = 3 * 64 * 4;
+constexpr int U2_SMEM_BYTES = 1024 + 4 * U2_A_PLANE + U2_W_BYTES + U2_ZT_BYTES + U2_BAR_BYTES + U2_STG_BYTES;
+static_assert(U2_SMEM_BYTES <= 232448, "conv_up2 shared memory exceeds the 227 KB opt-in limit");
+constexpr int U2_ROWS_PER_NBLK = 9 * 64;         // packed weight rows per block of 64 output channels
+
+// shift groups in issue order: N, TMEM column offset, A start offset (tile positions), weight region offset, 64-row units
+__host__ __device__ constexpr int u2_n(int sg) { return sg == 0 ? 256 : (sg == 3 ? 64 : 128); }
+__host__ __device__ constexpr int u2_col(int sg) { return sg < 2 ? 0 : 64; }
+__host__ __device__ constexpr int u2_aoff(int sg) { return sg == 0 ? U2_P + 1 : (sg == 1 ? U2_P : (sg == 2 ? 1 : 0)); }
+__host__ __device__ constexpr int u2_units(int sg) { return sg == 0 ? 4 : (sg == 3 ? 1 : 2); }
+__host__ __device__ constexpr int u2_ubase(int sg) { return sg == 0 ? 0 : (sg == 1 ? 4 : (sg == 2 ? 6 : 8)); }
+
+__device__ __forceinline__ float4 f4_fma(float a, const float4& x, const float4& acc) {
+    return make_float4(fmaf(a, x.x, acc.x), fmaf(a, x.y, acc.y), fmaf(a, x.z, acc.z), fmaf(a, x.w, acc.w));
+}
+__device__ __forceinline__ float4 f4_mul(float a, const float4& x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
+
+__global__ void __launch_bounds__(U2_THREADS, 1)
+conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ Up2Params P, const EpiParams epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_base = smem;                                  // [buf 2][plane hi/lo][U2_A_PX][128 B]
+    uint8_t* w_base = smem + 4 * U2_A_PLANE;                 // 9 units of [64][128 B]: S0 (4) | S1 (2) | S2 (2) | S3 (1)
+    float* zt = reinterpret_cast<float*>(w_base + U2_W_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(zt) + U2_ZT_BYTES);
+    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_empty = bars + 2;       // [2]
+    uint64_t* w_full = bars + 4;        // [4] one per shift group region
+    uint64_t* w_empty = bars + 8;       // [4]
+    uint64_t* t_full = bars + 12;       // [2]
+    uint64_t* t_empty = bars + 14;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + U2_BAR_BYTES);   // [3][64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kslabs = P.C / U2_KC;
+    const int nplanes = P.passes == 3 ? 2 : 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+            mbar_init(&t_full[s], 1);
+            mbar_init(&t_empty[s], U2_EPI_THREADS);
+        }
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(U2_REGS_DEC));
+        if (warp == 2) {
+            // ===================== halo-tile TMA producer =====================
+            if (elect_one()) {
+                int buf = 0;
+                uint32_t phase = 0;
+                const uint32_t tx_bytes = (uint32_t)nplanes * (uint32_t)(U2_A_BOX_ROWS * 128);
+                for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
+                    int m = tile / P.nblk;
+                    const int kx = m % P.tiles_x;
+                    m /= P.tiles_x;
+                    const int ky = m % P.tiles_y;
+                    const int n = m / P.tiles_y;
+                    const int x0 = U2_STEP_J * kx - 2, y0 = U2_STEP_I * ky - 2;     // box origin = tile origin - 1 (halo)
+                    for (int ks = 0; ks < kslabs; ++ks) {
+                        mbar_wait(&a_empty[buf], phase ^ 1);
+                        uint8_t* sa = a_base + buf * 2 * U2_A_PLANE;
+                        mbar_expect_tx(&a_full[buf], tx_bytes);
+                        tma_load_4d(sa, &maps.a_hi, &a_full[buf], ks * U2_KC, x0, y0, n);
+                        if (nplanes == 2) tma_load_4d(sa + U2_A_PLANE, &maps.a_lo, &a_full[buf], ks * U2_KC, x0, y0, n);
+                        buf ^= 1;
+                        if (buf == 0) phase ^= 1;
+                    }
+                }
+            }
+        } else if (warp == 0) {
+            // ===================== weight TMA producer =====================
+            if (elect_one()) {
+                uint32_t phase = 0;          // the four regions are used in lock step: one phase bit serves all
+                for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
+                    const int nb = tile % P.nblk;
+                    for (int ks = 0; ks < kslabs; ++ks) {
+                        for (int h = 0; h < nplanes; ++h) {
+                            const CUtensorMap* wm = h == 0 ? &maps.w_hi : &maps.w_lo;
+#pragma unroll 1
+                            for (int sg = 0; sg < 4; ++sg) {
+                                mbar_wait(&w_empty[sg], phase ^ 1);
+                                mbar_expect_tx(&w_full[sg], (uint32_t)(P.sg_units[sg] * U2_W_UNIT));
+                                for (int u = 0; u < P.sg_units[sg]; ++u) {
+                                    const int unit = P.sg_ubase[sg] + u;
+                                    tma_load_2d(w_base + unit * U2_W_UNIT, wm, &w_full[sg], ks * U2_KC, nb * U2_ROWS_PER_NBLK + unit * 64);
+                                }
+                            }
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ===================== MMA issuer =====================
+            if (elect_one()) {
+                constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+                const uint32_t a_lo0 = ((smem_u32(a_base) & 0x3FFFF) >> 4) | (1u << 16);
+                const uint32_t w_lo0 = ((smem_u32(w_base) & 0x3FFFF) >> 4) | (1u << 16);
+                constexpr uint32_t A_PLANE16 = U2_A_PLANE >> 4, K16 = 32 >> 4;
+                int buf = 0, acc = 0;
+                uint32_t a_phase = 0, w_phase = 0, acc_phase = 0;
+                for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
+                    for (int ks = 0; ks < kslabs; ++ks) {
+                        mbar_wait(&t_empty[acc], acc_phase ^ 1);
+                        mbar_wait(&a_full[buf], a_phase);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                        const uint32_t ah = a_lo0 + (uint32_t)buf * 2u * A_PLANE16, al = ah + A_PLANE16;
+#pragma unroll 1
+                        for (int h = 0; h < nplanes; ++h) {
+#pragma unroll 1
+                            for (int sg = 0; sg < 4; ++sg) {
+                                const uint32_t idesc = P.sg_idesc[sg];
+                                const uint32_t aoff16 = P.sg_aoff16[sg];
+                                const uint32_t wb = w_lo0 + P.sg_wb16[sg];
+                                const uint32_t dcol = d_tmem + P.sg_col[sg];
+                                mbar_wait(&w_full[sg], w_phase);
+                                tc_fence_after();
+#pragma unroll
+                                for (int k = 0; k < U2_KC / 16; ++k) {
+                                    const uint64_t db = ((uint64_t)DESC_HI << 32) | (wb + k * K16);
+                                    umma_f16(dcol, ((uint64_t)DESC_HI << 32) | (ah + aoff16 + k * K16), db, idesc, (h | sg | k) != 0);
+                                    if (h == 0 && nplanes == 2)
+                                        umma_f16(dcol, ((uint64_t)DESC_HI << 32) | (al + aoff16 + k * K16), db, idesc, 1);
+                                }
+                                umma_commit(&w_empty[sg]);
+                            }
+                            w_phase ^= 1;
+                        }
+                        umma_commit(&a_empty[buf]);
+                        umma_commit(&t_full[acc]);
+                        buf ^= 1;
+                        if (buf == 0) a_phase ^= 1;
+                        acc ^= 1;
+                        if (acc == 0) acc_phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(U2_REGS_INC));
+        // ===================== epilogue (warps 4..11) =====================
+        const int e = (int)threadIdx.x - (U2_THREADS - U2_EPI_THREADS);
+        const int q = warp & 3;                 // TMEM lane quarter
+        const int half = (warp - 4) >> 2;       // column half: parity blocks {(1,0),(0,0)} or {(0,1),(1,1)}
+        const int row = q * 32 + lane;          // tile position
+        const int r = row >> 4, c = row & 15;
+        // chained MMAs per chunk and column block: taps {2,4} (half 0) / {2,1} (half 1) x 4 k-steps x passes
+        const float mm = (float)(P.passes == 3 ? 12 : 4);
+        const float comp0 = 1.f + P.acc_comp * mm * 2.f;
+        const float comp1 = 1.f + P.acc_comp * mm * (half == 0 ? 4.f : 1.f);
+        // z-tile slots of my two parity blocks: z row 2r+py, column parity px = half, column index c
+        const int py0 = half == 0 ? 1 : 0, py1 = 1 - py0;
+        const int wpos0 = (((2 * r + py0) * 2 + half) * 16 + c) * 8;
+        const int wpos1 = (((2 * r + py1) * 2 + half) * 16 + c) * 8;
+        const int wsw = c & 7;
+        float4* zt4 = reinterpret_cast<float4*>(zt);
+        // blur role: 4 channels (q4) x output column pair x 6-row segment
+        const int q4 = e & 7, rest = e >> 3;
+        const int pair = rest % 13, seg = rest / 13;
+        const bool blur_active = rest < 26;
+        const int o1 = (16 + pair) * 8 + (q4 ^ (pair & 7));
+        const int o2 = (pair + 1) * 8 + (q4 ^ ((pair + 1) & 7));
+        const int o3 = (16 + pair + 1) * 8 + (q4 ^ ((pair + 1) & 7));
+        const int o4 = (pair + 2) * 8 + (q4 ^ ((pair + 2) & 7));
+        const int o5 = (16 + pair + 2) * 8 + (q4 ^ ((pair + 2) & 7));
+        const float fx0 = P.fx[0], fx1 = P.fx[1], fx2 = P.fx[2], fx3 = P.fx[3];
+        const float fy0 = P.fy[0], fy1 = P.fy[1], fy2 = P.fy[2], fy3 = P.fy[3];
+        const float nstr = epi.noise ? __ldg(epi.noise_strength) : 0.f;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
+            int m = tile / P.nblk;
+            const int nb = tile - m * P.nblk;
+            const int kx = m % P.tiles_x;
+            m /= P.tiles_x;
+            const int ky = m % P.tiles_y;
+            const int n = m / P.tiles_y;
+
+            float accv[128];
+            for (int ks = 0; ks < kslabs; ++ks) {
+                mbar_wait(&t_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + half * 128);
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    float v[16];
+                    tmem_ld16(taddr + p * 16, v);
+                    const float comp = p < 4 ? comp0 : comp1;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) accv[p * 16 + i] = ks == 0 ? v[i] * comp : fmaf(v[i], comp, accv[p * 16 + i]);
+                }
+                tc_fence_before();
+                mbar_arrive(&t_empty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                // the z tile / staging area is free again (previous round's or tile's readers are done)
+                asm volatile("bar.sync 1, %0;" ::"n"(U2_EPI_THREADS) : "memory");
+                if (g == 0 && e < 64) {
+                    const int o = nb * 64 + e;
+                    const long long no = (long long)n * P.Co + o;
+                    stg[e] = (epi.dcoef ? __ldg(epi.dcoef + no) : 1.f) * epi.wgain;
+                    stg[64 + e] = epi.bias ? __ldg(epi.bias + o) : 0.f;
+                    stg[128 + e] = epi.next_scale ? __ldg(epi.next_scale + no) : 1.f;
+                }
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                    const int i0 = g * 32 + qq * 4;
+                    zt4[wpos0 + (qq ^ wsw)] = make_float4(accv[i0], accv[i0 + 1], accv[i0 + 2], accv[i0 + 3]);
+                    zt4[wpos1 + (qq ^ wsw)] = make_float4(accv[64 + i0], accv[64 + i0 + 1], accv[64 + i0 + 2], accv[64 + i0 + 3]);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(U2_EPI_THREADS) : "memory");
+                if (!blur_active) continue;
+
+                const int lc = g * 32 + q4 * 4;                      // channel inside this block of 64
+                const int ch = nb * 64 + lc;
+                const int yb = U2_OWN_Y * ky + 6 * seg;              // first output row of my segment
+                const int xa = U2_OWN_X * kx + 2 * pair;             // my two output columns: xa, xa + 1
+                const bool va = xa < P.OW, vb = xa + 1 < P.OW;
+                const float4 sd = *reinterpret_cast<const float4*>(stg + lc);
+                const float4 sb = *reinterpret_cast<const float4*>(stg + 64 + lc);
+                const float4 sn = *reinterpret_cast<const float4*>(stg + 128 + lc);
+
+                // the skip planes and the noise of output row i are fetched at iteration t = i and consumed at t = i + 3:
+                // three rows of loads are in flight while the blur of the rows before them runs
+                uint2 sk[6][2][2];
+                float nz[6][2];
+
+                float4 hA[4], hB[4];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    if (t < 6) {
+                        const int y = yb + t;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const bool ok = y < P.OH && (j == 0 ? va : vb);
+                            const long long pix = ((long long)n * P.OH + y) * P.OW + xa + j;
+                            sk[t][j][0] = make_uint2(0u, 0u); sk[t][j][1] = make_uint2(0u, 0u);
+                            nz[t][j] = 0.f;
+                            if (ok) {
+                                if (epi.skip_hi) {
+                                    sk[t][j][0] = __ldg(reinterpret_cast<const uint2*>(epi.skip_hi + pix * P.Co + ch));
+                                    sk[t][j][1] = __ldg(reinterpret_cast<const uint2*>(epi.skip_lo + pix * P.Co + ch));
+                                }
+                                if (epi.noise) nz[t][j] = __ldg(epi.noise + (long long)n * epi.noise_sn + (long long)y * P.OW + xa + j) * nstr;
+                            }
+                        }
+                    }
+                    const float4* rowp = zt4 + (6 * seg + 1 + t) * 256;
+                    const float4 l1 = rowp[o1], l2 = rowp[o2], l3 = rowp[o3], l4 = rowp[o4], l5 = rowp[o5];
+                    hA[t & 3] = f4_fma(fx3, l4, f4_fma(fx2, l3, f4_fma(fx1, l2, f4_mul(fx0, l1))));
+                    hB[t & 3] = f4_fma(fx3, l5, f4_fma(fx2, l4, f4_fma(fx1, l3, f4_mul(fx0, l2))));
+                    if (t >= 3) {
+                        const int i = t - 3;
+                        const int y = yb + i;
+                        if (y < P.OH) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                if (!(j == 0 ? va : vb)) continue;
+                                const float4* hh = j == 0 ? hA : hB;
+                                const float4 o4v = f4_fma(fy3, hh[t & 3], f4_fma(fy2, hh[(t - 1) & 3], f4_fma(fy1, hh[(t - 2) & 3], f4_mul(fy0, hh[(t - 3) & 3]))));
+                                float v[4] = {fmaf(o4v.x, sd.x, nz[i][j]) + sb.x, fmaf(o4v.y, sd.y, nz[i][j]) + sb.y,
+                                              fmaf(o4v.z, sd.z, nz[i][j]) + sb.z, fmaf(o4v.w, sd.w, nz[i][j]) + sb.w};
+                                if (epi.act) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) v[k] = lrelu_agc(v[k], epi.act_alpha, epi.act_gain, epi.act_clamp);
+                                } else if (epi.act_gain != 1.f) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) v[k] *= epi.act_gain;
+                                }
+                                if (epi.skip_hi) {
+                                    const float2 a0 = unpack_h2(sk[i][j][0].x), a1 = unpack_h2(sk[i][j][0].y);
+                                    const float2 b0 = unpack_h2(sk[i][j][1].x), b1 = unpack_h2(sk[i][j][1].y);
+                                    v[0] += a0.x + b0.x; v[1] += a0.y + b0.y; v[2] += a1.x + b1.x; v[3] += a1.y + b1.y;
+                                }
+                                const long long pix = ((long long)n * P.OH + y) * P.OW + xa + j;
+                                if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + pix * P.Co + ch) = make_float4(v[0], v[1], v[2], v[3]);
+                                if (epi.out_hi) {
+                                    v[0] *= sn.x; v[1] *= sn.y; v[2] *= sn.z; v[3] *= sn.w;
+                                    __half h0, l0, h1, l1, h2, l2_, h3, l3_;
+                                    split_f32(v[0], h0, l0); split_f32(v[1], h1, l1); split_f32(v[2], h2, l2_); split_f32(v[3], h3, l3_);
+                                    *reinterpret_cast<uint2*>(epi.out_hi + pix * P.Co + ch) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+                                    *reinterpret_cast<uint2*>(epi.out_lo + pix * P.Co + ch) = make_uint2(pack_h2(l0, l1), pack_h2(l2_, l3_));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace shgan
+
+using namespace shgan;
+
+extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SHGAN_CHECK(d, "null descriptor");
+    SHGAN_CHECK(d->src_hi && d->src_lo && d->w_hi && d->w_lo, "null operand");
+    SHGAN_CHECK(d->N >= 0 && d->H >= 1 && d->W >= 1, "bad input size");
+    SHGAN_CHECK(d->C >= 64 && d->C % 64 == 0 && d->Co >= 64 && d->Co % 64 == 0, "C and Co must be multiples of 64");
+    SHGAN_CHECK((long long)d->N * d->C * d->H * d->W <= INT32_MAX, "input tensor is too large");
+    SHGAN_CHECK(4LL * d->N * d->Co * d->H * d->W <= INT32_MAX, "output tensor is too large");
+    SHGAN_CHECK(d->passes == 0 || d->passes == 1 || d->passes == 3, "passes must be 0, 1 or 3");
+    if (const char* m = check_epi(d->epi, d->Co)) SHGAN_CHECK(false, m);
+    SHGAN_CHECK(!d->epi.rgb_w, "the up-sampling convolution has no fused torgb");
+    if (d->N == 0) return 0;
+
+    Up2Params P;
+    P.N = d->N; P.H = d->H; P.W = d->W; P.C = d->C; P.Co = d->Co;
+    P.OH = 2 * d->H; P.OW = 2 * d->W;
+    P.tiles_x = ceil_div(P.OW, U2_OWN_X);
+    P.tiles_y = ceil_div(P.OH, U2_OWN_Y);
+    P.nblk = d->Co / 64;
+    const long long total = (long long)P.tiles_x * P.tiles_y * d->N * P.nblk;
+    SHGAN_CHECK(total <= INT32_MAX, "too many tiles");
+    P.total = (int)total;
+    for (int i = 0; i < 4; ++i) { P.fx[i] = d->fx[i]; P.fy[i] = d->fy[i] * d->gain; }
+    P.acc_comp = d->acc_comp == 0.f ? SHGAN_ACC_COMP_DEFAULT : (d->acc_comp < 0.f ? 0.f : d->acc_comp);
+    P.passes = d->passes == 0 ? 3 : d->passes;
+    for (int sg = 0; sg < 4; ++sg) {
+        P.sg_idesc[sg] = (1u << 4) | ((uint32_t)(u2_n(sg) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        P.sg_col[sg] = (uint32_t)u2_col(sg);
+        P.sg_aoff16[sg] = (uint32_t)u2_aoff(sg) * (128 / 16);
+        P.sg_wb16[sg] = (uint32_t)(u2_ubase(sg) * U2_W_UNIT) >> 4;
+        P.sg_units[sg] = u2_units(sg);
+        P.sg_ubase[sg] = u2_ubase(sg);
+    }
+
+    Up2Tmaps maps;
+    const uint64_t adims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    const uint32_t abox[4] = {(uint32_t)U2_KC, (uint32_t)U2_P, (uint32_t)(U2_ROWS + 1), 1u};
+    if (int e = encode_tmap(&maps.a_hi, d->src_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, adims, abox, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    if (int e = encode_tmap(&maps.a_lo, d->src_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, adims, abox, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    const uint64_t wdims[2] = {(uint64_t)d->C, (uint64_t)P.nblk * U2_ROWS_PER_NBLK};
+    const uint32_t wbox[2] = {(uint32_t)U2_KC, 64u};
+    if (int e = encode_tmap(&maps.w_hi, d->w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, wdims, wbox, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    if (int e = encode_tmap(&maps.w_lo, d->w_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, wdims, wbox, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+
+    static DeviceInit once;
+    int num_sms = 0;
+    if (int e = device_init(once, &num_sms, []() -> int {
+            SHGAN_CUDA(cudaFuncSetAttribute(conv_up2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
+            return 0;
+        })) return e;
+    const int grid = P.total < num_sms ? P.total : num_sms;
+    const EpiParams epi = make_epi(d->epi);
+    conv_up2_kernel<<<grid, U2_THREADS, U2_SMEM_BYTES, stream>>>(maps, P, epi);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}

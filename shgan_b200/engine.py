@@ -67,6 +67,7 @@ class GeneratorEngine:
         self.passes = passes
         self.impl = impl
         self.graphs = graphs      # replay the ~120 launches of a forward as one CUDA graph per (shape, mode)
+        self.fuse_up2 = True      # synthesis conv0: one shgan_conv_up2 launch instead of 4 RAW parity passes + the blur kernel
         self.overlap = True       # run the small off-critical-path kernels (mapping, SHU, torgb combine) on a side stream
         self._side = None
         self._sig = None
@@ -95,6 +96,7 @@ class GeneratorEngine:
         f = P.setup_filter([1, 3, 3, 1]) if f is None else f
         self.f = f.detach().to(dev, torch.float32).contiguous()               # as stored (upsample2d flips it itself)
         self.f_applied = self.f.flip([0, 1]).contiguous()                     # correlation taps of upfirdn2d(flip_filter=False)
+        self.f_sep = P.separable_taps(self.f_applied)                         # (fy, fx) when the blur is rank 1 (it always is: [1,3,3,1])
 
         # mapping
         m = G.mapping
@@ -150,12 +152,13 @@ class GeneratorEngine:
         def syn_layer(l, name, widx):
             w_hat, wsq = P.demod_weight(l.weight)
             wh, wl = P.pack_conv_weight(w_hat)
+            up2 = P.pack_up2_weight(w_hat) if (getattr(l, 'up', 1) == 2 and w_hat.shape[0] % 64 == 0 and w_hat.shape[2] == 3) else None
             self.style_layers.append(dict(name=name, widx=widx, aw=l.affine.weight.detach(), ab=l.affine.bias.detach(),
                                           again=float(l.affine.weight_gain), demod=True, wsq=wsq, pre_scale=1.0,
                                           ci=l.weight.shape[1], co=l.weight.shape[0]))
             return dict(w_hi=wh, w_lo=wl, bias=l.bias.detach(), noise_const=l.noise_const.detach().contiguous(),
                         noise_strength=l.noise_strength.detach(), ci=l.weight.shape[1], co=l.weight.shape[0],
-                        res=l.resolution, use_noise=l.use_noise)
+                        res=l.resolution, use_noise=l.use_noise, up2=up2)
 
         def rgb_layer(l, name, widx):
             w = l.weight.detach()
@@ -412,17 +415,21 @@ class GeneratorEngine:
                 # conv0: stride-2 transposed conv as four parity passes at algorithmic cost, then blur + epilogue
                 L0, name0 = d['conv0'], f'b{r}.conv0'
                 h = r // 2
-                z = self._f32(f's{r}.z', n, 2 * h + 1, 2 * h + 1, L0['co'])
-                for py in range(2):
-                    for px in range(2):
-                        self._conv([x], L0, P.taps_up2(py, px), P.up2_pass_size(h, py), P.up2_pass_size(h, px),
-                                   raw=(z, 2, 2, py, px))
                 nz, sn = noise[name0]
                 y = self._planes(f's{r}.mid', n, r, r, L0['co'])
                 epi = K.make_epilogue(dcoef=st[name0][1], noise=nz, noise_sn=sn, noise_strength=L0['noise_strength'],
                                       bias=L0['bias'], act=act.on, act_alpha=act.alpha, act_gain=act.gain, act_clamp=act.clamp,
                                       skip=feats[r], next_scale=st[f'b{r}.conv1'][0], out=y)
-                K.fir_nhwc(z, self.f_applied, 4.0, (1, 1, 1, 1), epi)
+                if self.fuse_up2 and self.impl == 0 and L0['up2'] is not None and self.f_sep is not None:
+                    # one launch: transposed conv (4 parities stacked along N) + blur + epilogue, z never leaves the SM
+                    K.conv_up2(x, L0['up2'][0], L0['up2'][1], self.f_sep[1], self.f_sep[0], 4.0, epi, passes=self.passes)
+                else:
+                    z = self._f32(f's{r}.z', n, 2 * h + 1, 2 * h + 1, L0['co'])
+                    for py in range(2):
+                        for px in range(2):
+                            self._conv([x], L0, P.taps_up2(py, px), P.up2_pass_size(h, py), P.up2_pass_size(h, px),
+                                       raw=(z, 2, 2, py, px))
+                    K.fir_nhwc(z, self.f_applied, 4.0, (1, 1, 1, 1), epi)
                 x = y
                 L, name = d['conv1'], f'b{r}.conv1'
             nz, sn = noise[name]

@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, Epilogue
+from ._lib import ConvDesc, Epilogue, Up2Desc
 
 SQRT2 = math.sqrt(2.0)
 ACC_COMP = float(os.environ.get('SHGAN_ACC_COMP', '0'))   # development override of shgan_conv_desc::acc_comp
@@ -199,6 +199,25 @@ def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, pa
     d.acc_comp = ACC_COMP if acc_comp is None else acc_comp    # 0 = library default, < 0 = off (include/shgan_b200.h)
     lib = _lib.load()
     _lib.check(lib.shgan_conv_igemm(C.byref(d), _stream()), 'shgan_conv_igemm')
+
+
+@_on_tensor_device
+def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None):
+    """Fused up-sampling convolution (shgan_conv_up2): src Planes [N,H,W,C]; w_hi/w_lo fp16 [Co/64, 9, 64, C] from
+    packing.pack_up2_weight; fx/fy: the separable blur taps as applied (4 floats each); epi: Epilogue at [N,2H,2W,Co]."""
+    d = Up2Desc()
+    n, h, w, c = src.shape
+    d.src_hi = _p(src.hi); d.src_lo = _p(src.lo)
+    d.N = n; d.H = h; d.W = w; d.C = c; d.Co = w_hi.shape[0] * 64
+    d.w_hi = _p(w_hi); d.w_lo = _p(w_lo)
+    for i in range(4):
+        d.fx[i] = float(fx[i]); d.fy[i] = float(fy[i])
+    d.gain = float(gain)
+    d.epi = epi
+    d.passes = passes
+    d.acc_comp = ACC_COMP if acc_comp is None else acc_comp
+    lib = _lib.load()
+    _lib.check(lib.shgan_conv_up2(C.byref(d), _stream()), 'shgan_conv_up2')
 
 
 def conv_num_nblocks(co, block_n=0):

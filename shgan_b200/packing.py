@@ -24,6 +24,32 @@ def pack_conv_weight(w):
     return split_f16(wt)
 
 
+UP2_TAP_ORDER = (3, 0, 1, 4, 5, 2, 6, 7, 8)
+
+
+def pack_up2_weight(w):
+    """[Co,Ci,3,3] fp32 -> (w_hi, w_lo) fp16 [Co/64, 9, 64, Ci] for shgan_conv_up2: per block of 64 output channels the
+    nine taps in the order its stacked-N MMAs read them (include/shgan_b200.h): operand shift (0,0) feeds parities
+    (1,0) (0,0) (0,1) (1,1) with taps 3,0,1,4; shift (0,-1) feeds (1,0) (0,0) with 5,2; shift (-1,0) feeds (0,0) (0,1)
+    with 6,7; shift (-1,-1) feeds (0,0) with 8 (tap = ky*3 + kx of the un-flipped weight, cf. taps_up2)."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3 and co % 64 == 0
+    wt = w.detach().to(torch.float32).permute(2, 3, 0, 1).reshape(9, co // 64, 64, ci)      # [tap, blk, o, i]
+    wt = wt[list(UP2_TAP_ORDER)].permute(1, 0, 2, 3).contiguous()                            # [blk, slot, o, i]
+    return split_f16(wt)
+
+
+def separable_taps(f):
+    """4x4 filter (as applied) -> (fy, fx) python lists with outer(fy, fx) == f, or None if f is not rank 1."""
+    f = torch.as_tensor(f, dtype=torch.float64).cpu()
+    if f.ndim != 2 or tuple(f.shape) != (4, 4) or float(f.sum()) == 0.0:
+        return None
+    fy, fx = f.sum(dim=1), f.sum(dim=0) / f.sum()
+    if float((torch.outer(fy, fx) - f).abs().max()) > 1e-7 * float(f.abs().max()):
+        return None
+    return [float(v) for v in fy], [float(v) for v in fx]
+
+
 def demod_weight(w):
     """Weight pre-normalisation of modulated_conv2d (stylegan.py:146) and the per-(o,i) energy table
     wsq[o,i] = sum_k w_hat[o,i,k]^2 from which the demodulation coefficients are formed (stylegan.py:155)."""

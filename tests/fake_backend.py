@@ -89,7 +89,7 @@ def conv_num_nblocks(co, block_n=0):
     return co // 32
 
 
-def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0):
+def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0, acc_comp=None):
     n, _, _, c = srcs[0].shape
     w = w_hi.float() + w_lo.float()          # [T, Co, C]
     co = w.shape[1]
@@ -110,6 +110,29 @@ def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, pa
         z[:, zoy:zoy + (oh - 1) * zsy + 1:zsy, zox:zox + (ow - 1) * zsx + 1:zsx] = acc
     else:
         _apply_epi(acc, epi, _block_n(co, block_n))
+
+
+def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None):
+    """shgan_conv_up2 following the header text literally: z[n,2i+ky,2j+kx,o] += src[n,i,j,c] * w[ky*3+kx,o,c], then
+    out[y,x] = gain * sum fy[a] fx[b] z[y+a-1, x+b-1] (zero outside), then the epilogue."""
+    x = src.float()
+    n, h, w, c = x.shape
+    blocks = w_hi.shape[0]
+    co = blocks * 64
+    wp = w_hi.float() + w_lo.float()                      # [blk, slot, 64, C], slot -> tap {3,0,1,4,5,2,6,7,8}
+    order = (3, 0, 1, 4, 5, 2, 6, 7, 8)
+    wt = torch.zeros((9, co, c), dtype=torch.float32)
+    for slot, tap in enumerate(order):
+        wt[tap] = wp[:, slot].reshape(co, c)
+    z = torch.zeros((n, 2 * h + 1 + 2, 2 * w + 1 + 2, co), dtype=torch.float32)      # one zero ring = z outside its support
+    for ky in range(3):
+        for kx in range(3):
+            z[:, 1 + ky:1 + ky + 2 * h:2, 1 + kx:1 + kx + 2 * w:2] += x @ wt[ky * 3 + kx].T
+    acc = torch.zeros((n, 2 * h, 2 * w, co), dtype=torch.float32)
+    for a in range(4):
+        for b in range(4):
+            acc += float(fy[a]) * float(fx[b]) * gain * z[:, a:a + 2 * h, b:b + 2 * w]
+    _apply_epi(acc, epi, 64)
 
 
 def fir_nhwc(src, f, gain, pads, epi, parity_split=False):
@@ -253,7 +276,7 @@ def shu_fwd(x, conv0_w, conv0_b, df1_w, cw, gauss, outs, lowest_res, workspace=N
 def install(monkeypatch):
     """Patch shgan_b200.kernels (and the engine's device check) with the CPU emulation."""
     import shgan_b200.engine as E
-    for name in ['make_epilogue', 'conv_num_nblocks', 'conv_igemm', 'fir_nhwc', 'nchw_to_planes', 'planes_to_nchw',
+    for name in ['make_epilogue', 'conv_num_nblocks', 'conv_igemm', 'conv_up2', 'fir_nhwc', 'nchw_to_planes', 'planes_to_nchw',
                  'planes_add_nchw', 'nhwc_to_nchw_f32', 'fromrgb', 'torgb_combine', 'mbstd_append', 'dense', 'normalize_2nd_moment',
                  'style_prep', 'style_prep_batched', 'shu_workspace_bytes', 'shu_fwd']:
         monkeypatch.setattr(K, name, globals()[name])

@@ -253,3 +253,70 @@ def test_generator_then_discriminator_tc_step():
     fake_ref = x[:, 1:4] * mr + img_ref * (1 - mr)
     ref = O.discriminator(sd_d, np.concatenate([x[:, 0:1], fake_ref], axis=1).astype(np.float32), 128)
     assert np.abs(logits - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------------------- fused up-sampling convolution
+def _up2_reference(x, w, fy, fx, gain):
+    """fp64 torch: conv_transpose2d(stride 2) with the un-flipped weights, then the separable blur with zero pad 1."""
+    n, c, h, wd = x.shape
+    z = torch.nn.functional.conv_transpose2d(x.double(), w.double().permute(1, 0, 2, 3), stride=2)      # [n,co,2h+1,2w+1]
+    f = torch.outer(torch.tensor(fy, dtype=torch.float64), torch.tensor(fx, dtype=torch.float64)).to(x.device) * gain
+    co = z.shape[1]
+    return torch.nn.functional.conv2d(z, f[None, None].expand(co, 1, 4, 4), padding=1, groups=co)        # correlation, as applied
+
+
+UP2_SHAPES = [(2, 64, 64, 8, 8), (1, 128, 64, 20, 23), (2, 64, 128, 13, 7), (1, 256, 192, 4, 4), (3, 64, 64, 1, 2), (2, 192, 64, 33, 40)]
+
+
+@pytest.mark.parametrize('shape', UP2_SHAPES, ids=[str(s) for s in UP2_SHAPES])
+@pytest.mark.parametrize('passes', [3, 1])
+def test_conv_up2_tc_vs_fp64(shape, passes):
+    from shgan_b200 import kernels as K, packing as P
+    n, ci, co, h, wd = shape
+    g = torch.Generator().manual_seed(ci * 7 + co + h)
+    x = torch.randn(n, ci, h, wd, generator=g).to(DEV)
+    w = (torch.randn(co, ci, 3, 3, generator=g) / (3 * ci ** 0.5)).to(DEV)
+    fy, fx = [0.25, 0.75, 0.75, 0.25], [0.125, 0.375, 0.375, 0.125]
+    fy = [1.0, 2.5, 3.0, 0.5]                                  # asymmetric taps: catches any flip / transposition of the blur
+    fx = [0.5, 3.0, 2.0, 1.5]
+    ref = _up2_reference(x, w, fy, fx, 4.0 / 49.0)
+    xp = K.nchw_to_planes(x)
+    uh, ul = P.pack_up2_weight(w)
+    # raw accumulator path (identity epilogue)
+    y32 = torch.empty((n, 2 * h, 2 * wd, co), device=DEV)
+    K.conv_up2(xp, uh, ul, fx, fy, 4.0 / 49.0, K.make_epilogue(out_f32=y32), passes=passes)
+    tol = 1e-5 if passes == 3 else 5e-3
+    assert relerr(y32.permute(0, 3, 1, 2).cpu().numpy(), ref.cpu().numpy()) <= tol
+    # full epilogue: demod, per-sample noise, bias, lrelu + clamp, skip, next-layer style; planes + fp32 outputs
+    dc = (0.5 + torch.rand(n, co, generator=g)).to(DEV)
+    nzv = torch.randn(n, 1, 2 * h, 2 * wd, generator=g).to(DEV)
+    strength = torch.tensor(0.3, device=DEV)
+    bias = torch.randn(co, generator=g).to(DEV)
+    skip = torch.randn(n, co, 2 * h, 2 * wd, generator=g).to(DEV)
+    ns = (0.5 + torch.rand(n, co, generator=g)).to(DEV)
+    out = K.Planes.empty(n, 2 * h, 2 * wd, co, DEV)
+    K.conv_up2(xp, uh, ul, fx, fy, 4.0 / 49.0,
+               K.make_epilogue(dcoef=dc, wgain=0.7, noise=nzv, noise_sn=4 * h * wd, noise_strength=strength, bias=bias, act=True,
+                               act_alpha=0.2, act_gain=2 ** 0.5, act_clamp=3.0, skip=K.nchw_to_planes(skip), next_scale=ns, out=out,
+                               out_f32=y32), passes=passes)
+    v = ref * dc[:, :, None, None] * 0.7 + nzv * 0.3 + bias[None, :, None, None]
+    v = (torch.where(v >= 0, v, v * 0.2) * 2 ** 0.5).clamp(-3.0, 3.0)
+    sk = K.planes_to_nchw(K.nchw_to_planes(skip)).double()
+    v = v + sk
+    assert relerr(y32.permute(0, 3, 1, 2).cpu().numpy(), v.cpu().numpy()) <= (2e-5 if passes == 3 else 5e-3)
+    got = K.planes_to_nchw(out).double()
+    assert relerr(got.cpu().numpy(), (v * ns[:, :, None, None]).cpu().numpy()) <= (2e-5 if passes == 3 else 5e-3)
+
+
+def test_generator_tc_fused_up2_equals_unfused():
+    """The fused up-sampling launch against the 4 RAW passes + blur kernel it replaces, on the full 256^2 model."""
+    sd = O.synthetic_state_dict(256, seed=4)
+    G = H.build_generator(256, sd, device=DEV)
+    x, z = O.synthetic_inputs(2, 256, seed=4)
+    eng = G.engine(impl=0)
+    a = G(t(x), t(z), None, noise_mode='const').cpu().numpy()
+    eng.fuse_up2 = False
+    eng._graphs = {}
+    b = G(t(x), t(z), None, noise_mode='const').cpu().numpy()
+    eng.fuse_up2 = True
+    assert np.abs(a - b).max() <= 2e-4 * max(1.0, np.abs(b).max()), np.abs(a - b).max()
