@@ -87,7 +87,9 @@ __device__ __forceinline__ float4 f4_mul(float a, const float4& x) { return make
 __global__ void __launch_bounds__(U2_THREADS, 1)
 conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ Up2Params P, const EpiParams epi) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // aligned by pointer arithmetic on the __shared__ array (not an integer round trip), so that the compiler keeps the
+    // shared address space and emits LDS/STS with immediate offsets for the z tile
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_base = smem;                                  // [buf 2][plane hi/lo][U2_A_PX][128 B]
     uint8_t* w_base = smem + 4 * U2_A_PLANE;                 // 9 units of [64][128 B]: S0 (4) | S1 (2) | S2 (2) | S3 (1)
     float* zt = reinterpret_cast<float*>(w_base + U2_W_BYTES);
@@ -236,24 +238,33 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
         const float mm = (float)(P.passes == 3 ? 12 : 4);
         const float comp0 = 1.f + P.acc_comp * mm * 2.f;
         const float comp1 = 1.f + P.acc_comp * mm * (half == 0 ? 4.f : 1.f);
-        // z-tile slots of my two parity blocks: z row 2r+py, column parity px = half, column index c
+        // z-tile slots (float4 index) of my two parity blocks: z row 2r+py, column parity px = half, column index c;
+        // channel quad qq of a position lives in slot qq ^ (c & 7)
         const int py0 = half == 0 ? 1 : 0, py1 = 1 - py0;
-        const int wpos0 = (((2 * r + py0) * 2 + half) * 16 + c) * 8;
-        const int wpos1 = (((2 * r + py1) * 2 + half) * 16 + c) * 8;
+        float4* const zt4 = reinterpret_cast<float4*>(zt);
+        float4* const zw0 = zt4 + (((2 * r + py0) * 2 + half) * 16 + c) * 8;
+        float4* const zw1 = zt4 + (((2 * r + py1) * 2 + half) * 16 + c) * 8;
         const int wsw = c & 7;
-        float4* zt4 = reinterpret_cast<float4*>(zt);
-        // blur role: 4 channels (q4) x output column pair x 6-row segment
-        const int q4 = e & 7, rest = e >> 3;
-        const int pair = rest % 13, seg = rest / 13;
-        const bool blur_active = rest < 26;
-        const int o1 = (16 + pair) * 8 + (q4 ^ (pair & 7));
-        const int o2 = (pair + 1) * 8 + (q4 ^ ((pair + 1) & 7));
-        const int o3 = (16 + pair + 1) * 8 + (q4 ^ ((pair + 1) & 7));
-        const int o4 = (pair + 2) * 8 + (q4 ^ ((pair + 2) & 7));
-        const int o5 = (16 + pair + 2) * 8 + (q4 ^ ((pair + 2) & 7));
+        // blur role: thread = 4 channels (quad q4) of one output column ox, walking the 15 z rows of the tile
+        const int q4 = e & 7, ox = e >> 3;
+        const bool blur_active = ox < U2_OWN_X;
+        const float4* zr[4];                    // the four z columns ox + 1 + b of z row 1
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int X = ox + 1 + b, cc = X >> 1;
+            zr[b] = zt4 + 256 + (((X & 1) * 16 + cc) * 8 + (q4 ^ (cc & 7)));
+        }
         const float fx0 = P.fx[0], fx1 = P.fx[1], fx2 = P.fx[2], fx3 = P.fx[3];
         const float fy0 = P.fy[0], fy1 = P.fy[1], fy2 = P.fy[2], fy3 = P.fy[3];
-        const float nstr = epi.noise ? __ldg(epi.noise_strength) : 0.f;
+        // pointwise parameters, normalised once: lrelu(u) * gain == lrelu(u * gain) for gain > 0, so the gain is folded into
+        // the staged scale / bias / noise; no activation = alpha 1; no clamp = +inf
+        const float gain_e = epi.act_gain;
+        const float alpha_e = epi.act ? epi.act_alpha : 1.f;
+        const float clamp_e = (epi.act && epi.act_clamp > 0.f) ? epi.act_clamp : __int_as_float(0x7f800000);
+        const float nstr = epi.noise ? __ldg(epi.noise_strength) * gain_e : 0.f;
+        const bool has_skip = epi.skip_hi != nullptr, has_noise = epi.noise != nullptr, has_f32 = epi.out_f32 != nullptr,
+                   has_planes = epi.out_hi != nullptr;
+        const int row_elems = P.OW * P.Co;      // elements between vertically adjacent pixels (tensor sizes are < 2^31)
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
@@ -283,6 +294,9 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                 if (acc == 0) acc_phase ^= 1;
             }
 
+            const int y0 = U2_OWN_Y * ky, x = U2_OWN_X * kx + ox;       // first output row of the tile, my output column
+            const int rows_valid = P.OH - y0 < U2_OWN_Y ? P.OH - y0 : U2_OWN_Y;
+            const bool col_valid = blur_active && x < P.OW;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 // the z tile / staging area is free again (previous round's or tile's readers are done)
@@ -290,89 +304,77 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                 if (g == 0 && e < 64) {
                     const int o = nb * 64 + e;
                     const long long no = (long long)n * P.Co + o;
-                    stg[e] = (epi.dcoef ? __ldg(epi.dcoef + no) : 1.f) * epi.wgain;
-                    stg[64 + e] = epi.bias ? __ldg(epi.bias + o) : 0.f;
+                    stg[e] = (epi.dcoef ? __ldg(epi.dcoef + no) : 1.f) * epi.wgain * gain_e;
+                    stg[64 + e] = epi.bias ? __ldg(epi.bias + o) * gain_e : 0.f;
                     stg[128 + e] = epi.next_scale ? __ldg(epi.next_scale + no) : 1.f;
                 }
 #pragma unroll
                 for (int qq = 0; qq < 8; ++qq) {
                     const int i0 = g * 32 + qq * 4;
-                    zt4[wpos0 + (qq ^ wsw)] = make_float4(accv[i0], accv[i0 + 1], accv[i0 + 2], accv[i0 + 3]);
-                    zt4[wpos1 + (qq ^ wsw)] = make_float4(accv[64 + i0], accv[64 + i0 + 1], accv[64 + i0 + 2], accv[64 + i0 + 3]);
+                    zw0[qq ^ wsw] = make_float4(accv[i0], accv[i0 + 1], accv[i0 + 2], accv[i0 + 3]);
+                    zw1[qq ^ wsw] = make_float4(accv[64 + i0], accv[64 + i0 + 1], accv[64 + i0 + 2], accv[64 + i0 + 3]);
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(U2_EPI_THREADS) : "memory");
-                if (!blur_active) continue;
+                if (!col_valid) continue;
 
-                const int lc = g * 32 + q4 * 4;                      // channel inside this block of 64
-                const int ch = nb * 64 + lc;
-                const int yb = U2_OWN_Y * ky + 6 * seg;              // first output row of my segment
-                const int xa = U2_OWN_X * kx + 2 * pair;             // my two output columns: xa, xa + 1
-                const bool va = xa < P.OW, vb = xa + 1 < P.OW;
+                const int lc = g * 32 + q4 * 4;                      // my 4 channels inside this block of 64
                 const float4 sd = *reinterpret_cast<const float4*>(stg + lc);
                 const float4 sb = *reinterpret_cast<const float4*>(stg + 64 + lc);
                 const float4 sn = *reinterpret_cast<const float4*>(stg + 128 + lc);
+                // element index of (n, y0, x, first channel); rows advance by row_elems
+                const int e0 = ((n * P.OH + y0) * P.OW + x) * P.Co + nb * 64 + lc;
+                const __half* p_sh = epi.skip_hi + e0;
+                const __half* p_sl = epi.skip_lo + e0;
+                __half* p_oh = epi.out_hi + e0;
+                __half* p_ol = epi.out_lo + e0;
+                float* p_of = epi.out_f32 + e0;
+                const float* p_nz = epi.noise + ((long long)n * epi.noise_sn + (long long)y0 * P.OW + x);
 
-                // the skip planes and the noise of output row i are fetched at iteration t = i and consumed at t = i + 3:
-                // three rows of loads are in flight while the blur of the rows before them runs
-                uint2 sk[6][2][2];
-                float nz[6][2];
-
-                float4 hA[4], hB[4];
+                // skip planes / noise of output row i: fetched at step t = i, consumed at t = i + 3
+                uint2 skh[12], skl[12];
+                float nz[12];
+                float4 h[4];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    if (t < 6) {
-                        const int y = yb + t;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const bool ok = y < P.OH && (j == 0 ? va : vb);
-                            const long long pix = ((long long)n * P.OH + y) * P.OW + xa + j;
-                            sk[t][j][0] = make_uint2(0u, 0u); sk[t][j][1] = make_uint2(0u, 0u);
-                            nz[t][j] = 0.f;
-                            if (ok) {
-                                if (epi.skip_hi) {
-                                    sk[t][j][0] = __ldg(reinterpret_cast<const uint2*>(epi.skip_hi + pix * P.Co + ch));
-                                    sk[t][j][1] = __ldg(reinterpret_cast<const uint2*>(epi.skip_lo + pix * P.Co + ch));
-                                }
-                                if (epi.noise) nz[t][j] = __ldg(epi.noise + (long long)n * epi.noise_sn + (long long)y * P.OW + xa + j) * nstr;
+                for (int t = 0; t < 15; ++t) {
+                    if (t < 12) {
+                        skh[t] = make_uint2(0u, 0u); skl[t] = make_uint2(0u, 0u); nz[t] = 0.f;
+                        if (t < rows_valid) {
+                            if (has_skip) {
+                                skh[t] = __ldg(reinterpret_cast<const uint2*>(p_sh + t * row_elems));
+                                skl[t] = __ldg(reinterpret_cast<const uint2*>(p_sl + t * row_elems));
                             }
+                            if (has_noise) nz[t] = __ldg(p_nz + t * P.OW) * nstr;
                         }
                     }
-                    const float4* rowp = zt4 + (6 * seg + 1 + t) * 256;
-                    const float4 l1 = rowp[o1], l2 = rowp[o2], l3 = rowp[o3], l4 = rowp[o4], l5 = rowp[o5];
-                    hA[t & 3] = f4_fma(fx3, l4, f4_fma(fx2, l3, f4_fma(fx1, l2, f4_mul(fx0, l1))));
-                    hB[t & 3] = f4_fma(fx3, l5, f4_fma(fx2, l4, f4_fma(fx1, l3, f4_mul(fx0, l2))));
+                    const float4 l0 = zr[0][t * 256], l1 = zr[1][t * 256], l2 = zr[2][t * 256], l3 = zr[3][t * 256];
+                    h[t & 3] = f4_fma(fx3, l3, f4_fma(fx2, l2, f4_fma(fx1, l1, f4_mul(fx0, l0))));
                     if (t >= 3) {
                         const int i = t - 3;
-                        const int y = yb + i;
-                        if (y < P.OH) {
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                if (!(j == 0 ? va : vb)) continue;
-                                const float4* hh = j == 0 ? hA : hB;
-                                const float4 o4v = f4_fma(fy3, hh[t & 3], f4_fma(fy2, hh[(t - 1) & 3], f4_fma(fy1, hh[(t - 2) & 3], f4_mul(fy0, hh[(t - 3) & 3]))));
-                                float v[4] = {fmaf(o4v.x, sd.x, nz[i][j]) + sb.x, fmaf(o4v.y, sd.y, nz[i][j]) + sb.y,
-                                              fmaf(o4v.z, sd.z, nz[i][j]) + sb.z, fmaf(o4v.w, sd.w, nz[i][j]) + sb.w};
-                                if (epi.act) {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) v[k] = lrelu_agc(v[k], epi.act_alpha, epi.act_gain, epi.act_clamp);
-                                } else if (epi.act_gain != 1.f) {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) v[k] *= epi.act_gain;
-                                }
-                                if (epi.skip_hi) {
-                                    const float2 a0 = unpack_h2(sk[i][j][0].x), a1 = unpack_h2(sk[i][j][0].y);
-                                    const float2 b0 = unpack_h2(sk[i][j][1].x), b1 = unpack_h2(sk[i][j][1].y);
-                                    v[0] += a0.x + b0.x; v[1] += a0.y + b0.y; v[2] += a1.x + b1.x; v[3] += a1.y + b1.y;
-                                }
-                                const long long pix = ((long long)n * P.OH + y) * P.OW + xa + j;
-                                if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + pix * P.Co + ch) = make_float4(v[0], v[1], v[2], v[3]);
-                                if (epi.out_hi) {
-                                    v[0] *= sn.x; v[1] *= sn.y; v[2] *= sn.z; v[3] *= sn.w;
-                                    __half h0, l0, h1, l1, h2, l2_, h3, l3_;
-                                    split_f32(v[0], h0, l0); split_f32(v[1], h1, l1); split_f32(v[2], h2, l2_); split_f32(v[3], h3, l3_);
-                                    *reinterpret_cast<uint2*>(epi.out_hi + pix * P.Co + ch) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-                                    *reinterpret_cast<uint2*>(epi.out_lo + pix * P.Co + ch) = make_uint2(pack_h2(l0, l1), pack_h2(l2_, l3_));
-                                }
+                        if (i < rows_valid) {
+                            const float4 o = f4_fma(fy3, h[t & 3], f4_fma(fy2, h[(t - 1) & 3], f4_fma(fy1, h[(t - 2) & 3], f4_mul(fy0, h[(t - 3) & 3]))));
+                            float v0 = fmaf(o.x, sd.x, nz[i]) + sb.x, v1 = fmaf(o.y, sd.y, nz[i]) + sb.y;
+                            float v2 = fmaf(o.z, sd.z, nz[i]) + sb.z, v3 = fmaf(o.w, sd.w, nz[i]) + sb.w;
+                            v0 = fminf(fmaxf(fmaxf(v0, v0 * alpha_e), -clamp_e), clamp_e);
+                            v1 = fminf(fmaxf(fmaxf(v1, v1 * alpha_e), -clamp_e), clamp_e);
+                            v2 = fminf(fmaxf(fmaxf(v2, v2 * alpha_e), -clamp_e), clamp_e);
+                            v3 = fminf(fmaxf(fmaxf(v3, v3 * alpha_e), -clamp_e), clamp_e);
+                            {
+                                const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&skh[i].x));
+                                const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&skh[i].y));
+                                const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&skl[i].x));
+                                const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&skl[i].y));
+                                v0 += a0.x + b0.x; v1 += a0.y + b0.y; v2 += a1.x + b1.x; v3 += a1.y + b1.y;
+                            }
+                            if (has_f32) *reinterpret_cast<float4*>(p_of + i * row_elems) = make_float4(v0, v1, v2, v3);
+                            if (has_planes) {
+                                v0 *= sn.x; v1 *= sn.y; v2 *= sn.z; v3 *= sn.w;
+                                const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                                const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+                                *reinterpret_cast<uint2*>(p_oh + i * row_elems) =
+                                    make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                                *reinterpret_cast<uint2*>(p_ol + i * row_elems) =
+                                    make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
                             }
                         }
                     }

@@ -31,7 +31,7 @@ def main():
     torch.cuda.synchronize()
     if a.layers:
         from shgan_b200 import kernels as K
-        names = ['conv_igemm', 'fir_nhwc', 'fromrgb', 'torgb_combine', 'dense', 'style_prep', 'shu_fwd', 'nchw_to_planes',
+        names = ['conv_igemm', 'conv_up2', 'fir_nhwc', 'fromrgb', 'torgb_combine', 'dense', 'style_prep', 'shu_fwd', 'nchw_to_planes',
                  'planes_to_nchw', 'planes_add_nchw', 'normalize_2nd_moment']
         acc = {}
         import shgan_b200.engine as E
@@ -48,6 +48,8 @@ def main():
                 if _nm == 'conv_igemm':
                     srcs, w_hi = args[0], args[1]
                     key = f'conv C{srcs[0].shape[3]}->{w_hi.shape[1]} {args[4]}x{args[5]} taps{len(args[3])} {"raw" if kw.get("raw") is not None else "act"}'
+                elif _nm == 'conv_up2':
+                    key = f'up2 C{args[0].shape[3]}->{args[1].shape[0] * 64} in {args[0].shape[1]}x{args[0].shape[2]}'
                 elif _nm == 'fir_nhwc':
                     key = f'fir {tuple(args[0].shape)}'
                 t = acc.setdefault(key, [0.0, 0])
