@@ -372,9 +372,9 @@ def main():
     comp_pin = torch.empty((batch, 3, res, res), dtype=torch.uint8).pin_memory()
 
     # ---- instrumentation: CUDA events around every launch of the three kernel families (current torch stream) ----
-    fam = {k: dict(events=[], work=0.0) for k in ('conv', 'fir', 'shu')}
+    fam = {k: dict(events=[], work=0.0) for k in ('conv', 'up2', 'fir', 'shu')}
     record = [False]
-    orig = dict(conv=K.conv_igemm, fir=K.fir_nhwc, shu=K.shu_fwd)
+    orig = dict(conv=K.conv_igemm, up2=K.conv_up2, fir=K.fir_nhwc, shu=K.shu_fwd)
 
     def timed(name, work_fn):
         fn = orig[name]
@@ -395,6 +395,10 @@ def main():
         n, _, _, c = srcs[0].shape
         return 2.0 * n * oh * ow * w_hi.shape[1] * c * len(taps)
 
+    def up2_work(src, w_hi, *a, **kw):
+        n, h, w, c = src.shape
+        return 2.0 * n * h * w * 9 * c * w_hi.shape[0] * 64            # transposed conv counted on its input grid
+
     def fir_work(src, f, gain, pads, epi, parity_split=False):
         n, ih, iw, c = src.shape
         oh, ow = ih + pads[2] + pads[3] - 3, iw + pads[0] + pads[1] - 3
@@ -406,6 +410,7 @@ def main():
         outs = a[5] if len(a) > 5 else kw['outs']
         return 4.0 * (x.numel() + sum(o.numel() for o in outs))
     K.conv_igemm, K.fir_nhwc, K.shu_fwd = timed('conv', conv_work), timed('fir', fir_work), timed('shu', shu_work)
+    K.conv_up2 = timed('up2', up2_work)
 
     if D is None:
         def step_device():
@@ -575,6 +580,10 @@ def main():
         imgs = batch * world * args.steps
         value = imgs / (ms / 1e3)
         steps = max(args.steps, 1)
+        # the convolution family = shgan_conv_igemm + the fused up-sampling convolution shgan_conv_up2
+        fam['conv']['work'] += fam['up2']['work']
+        fam['conv']['events'] += fam['up2']['events']
+        fam_ms['conv'] += fam_ms['up2']
         conv_tflops = fam['conv']['work'] / (fam_ms['conv'] / 1e3) / 1e12 if fam_ms['conv'] > 0 else 0.0
         tp = os.path.join(ROOT, 'profiles', 'conv_tc_traffic.json')
         traffic, traffic_src = None, None
@@ -597,6 +606,7 @@ def main():
                           launches_per_step=len(fam['conv']['events']) // steps,
                           algorithmic_gflop_per_step=fam['conv']['work'] / steps / 1e9,
                           kernel_ms_per_step=fam_ms['conv'] / steps, share_of_step=fam_ms['conv'] / ms_instr,
+                          up2_ms_per_step=fam_ms['up2'] / steps, up2_launches_per_step=len(fam['up2']['events']) // steps,
                           instrumented_ms_per_step=ms_instr / steps,
                           executed_tensor_tflops=conv_tflops * (3 if args.passes == 3 else 1),
                           note='achieved = algorithmic conv FLOPs / summed CUDA-event durations of the conv launches over the same K steps launched eagerly on one stream '

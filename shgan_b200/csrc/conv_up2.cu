@@ -45,6 +45,8 @@ struct Up2Params {
     float fx[4], fy[4];          // separable blur taps as applied (correlation order); gain folded into fy
     float acc_comp;
     int passes;
+    int chunk_slabs;             // 64-channel slabs chained in one TMEM accumulator (1, or 2 for C >= 256: fewer, longer chunks
+                                 // let the MMAs run four slabs ahead while the epilogue warps are busy with the blur)
     // per shift group (issue order), read by the single-thread producer / issuer loops from the constant bank:
     // instruction descriptor, TMEM column offset, A start offset and weight region offset in 16-byte descriptor units,
     // number of 64-row weight units and the first unit
@@ -65,7 +67,9 @@ constexpr int U2_A_PX = 152;                     // allocated positions per plan
 constexpr int U2_A_PLANE = U2_A_PX * 128;        // 19456 B, a multiple of 1024
 constexpr int U2_W_UNIT = 64 * 128;              // one [64 co x 64 ci] fp16 block
 constexpr int U2_W_BYTES = 9 * U2_W_UNIT;        // one plane of one slab: 72 KB
-constexpr int U2_ZT_BYTES = 16 * 2 * 16 * 32 * 4;    // 64 KB
+constexpr int U2_ZT_PITCH = 9;                   // float4 slots per z position: 8 channel quads + 1 pad (bank spreading)
+constexpr int U2_ZT_ROW = 32 * U2_ZT_PITCH;      // float4 slots per z row (32 z columns)
+constexpr int U2_ZT_BYTES = 16 * U2_ZT_ROW * 16; // 72 KB
 constexpr int U2_BAR_BYTES = 256;
 constexpr int U2_STG_BYTES = 3 * 64 * 4;
 constexpr int U2_SMEM_BYTES = 1024 + 4 * U2_A_PLANE + U2_W_BYTES + U2_ZT_BYTES + U2_BAR_BYTES + U2_STG_BYTES;
@@ -101,6 +105,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
     uint64_t* t_full = bars + 12;       // [2]
     uint64_t* t_empty = bars + 14;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    volatile int* epi_progress = reinterpret_cast<volatile int*>(bars + 17);   // index of the tile the epilogue is working on
     float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + U2_BAR_BYTES);   // [3][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,6 +113,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
     const int nplanes = P.passes == 3 ? 2 : 1;
 
     if (warp == 0 && lane == 0) {
+        *epi_progress = -1;
         prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&a_full[s], 1);
@@ -179,6 +185,35 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                     }
                 }
             }
+        } else if (warp == 3) {
+            // ===================== L2 prefetcher of the epilogue's global operands =====================
+            // The blur warps consume the skip planes (feats[res]) and the noise of a tile's 12 x 26 outputs straight from
+            // global memory; this otherwise idle warp pulls the NEXT tile's lines into L2 so that those loads are L2 hits.
+            if (epi.skip_hi || epi.noise) {
+                int k = 1;
+                for (int tile = blockIdx.x + gridDim.x; tile < P.total; tile += gridDim.x, ++k) {
+                    while (*epi_progress < k - 1) __nanosleep(500);     // stay exactly one tile ahead of the epilogue
+                    int m = tile / P.nblk;
+                    const int nb = tile - m * P.nblk;
+                    const int kx = m % P.tiles_x;
+                    m /= P.tiles_x;
+                    const int ky = m % P.tiles_y;
+                    const int n = m / P.tiles_y;
+                    for (int i = lane; i < U2_OWN_Y * U2_OWN_X; i += 32) {
+                        const int oy = i / U2_OWN_X, oxx = i - oy * U2_OWN_X;
+                        const int y = U2_OWN_Y * ky + oy, x = U2_OWN_X * kx + oxx;
+                        if (y < P.OH && x < P.OW) {
+                            const long long el = (((long long)n * P.OH + y) * P.OW + x) * P.Co + nb * 64;
+                            if (epi.skip_hi) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(epi.skip_hi + el));
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(epi.skip_lo + el));
+                            }
+                            if (epi.noise && (oxx & 7) == 0 && nb == 0)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(epi.noise + (long long)n * epi.noise_sn + (long long)y * P.OW + x));
+                        }
+                    }
+                }
+            }
         } else if (warp == 1) {
             // ===================== MMA issuer =====================
             if (elect_one()) {
@@ -190,7 +225,8 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                 uint32_t a_phase = 0, w_phase = 0, acc_phase = 0;
                 for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
                     for (int ks = 0; ks < kslabs; ++ks) {
-                        mbar_wait(&t_empty[acc], acc_phase ^ 1);
+                        const bool chunk_first = ks % P.chunk_slabs == 0, chunk_last = (ks + 1) % P.chunk_slabs == 0;
+                        if (chunk_first) mbar_wait(&t_empty[acc], acc_phase ^ 1);
                         mbar_wait(&a_full[buf], a_phase);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
@@ -208,7 +244,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
 #pragma unroll
                                 for (int k = 0; k < U2_KC / 16; ++k) {
                                     const uint64_t db = ((uint64_t)DESC_HI << 32) | (wb + k * K16);
-                                    umma_f16(dcol, ((uint64_t)DESC_HI << 32) | (ah + aoff16 + k * K16), db, idesc, (h | sg | k) != 0);
+                                    umma_f16(dcol, ((uint64_t)DESC_HI << 32) | (ah + aoff16 + k * K16), db, idesc, (h | sg | k) != 0 || !chunk_first);
                                     if (h == 0 && nplanes == 2)
                                         umma_f16(dcol, ((uint64_t)DESC_HI << 32) | (al + aoff16 + k * K16), db, idesc, 1);
                                 }
@@ -217,11 +253,13 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                             w_phase ^= 1;
                         }
                         umma_commit(&a_empty[buf]);
-                        umma_commit(&t_full[acc]);
                         buf ^= 1;
                         if (buf == 0) a_phase ^= 1;
-                        acc ^= 1;
-                        if (acc == 0) acc_phase ^= 1;
+                        if (chunk_last) {
+                            umma_commit(&t_full[acc]);
+                            acc ^= 1;
+                            if (acc == 0) acc_phase ^= 1;
+                        }
                     }
                 }
             }
@@ -235,25 +273,20 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
         const int row = q * 32 + lane;          // tile position
         const int r = row >> 4, c = row & 15;
         // chained MMAs per chunk and column block: taps {2,4} (half 0) / {2,1} (half 1) x 4 k-steps x passes
-        const float mm = (float)(P.passes == 3 ? 12 : 4);
+        const float mm = (float)((P.passes == 3 ? 12 : 4) * P.chunk_slabs);
         const float comp0 = 1.f + P.acc_comp * mm * 2.f;
         const float comp1 = 1.f + P.acc_comp * mm * (half == 0 ? 4.f : 1.f);
-        // z-tile slots (float4 index) of my two parity blocks: z row 2r+py, column parity px = half, column index c;
-        // channel quad qq of a position lives in slot qq ^ (c & 7)
+        // z-tile slots of my two parity blocks: z row 2r+py, z column 2c+half; a position holds its 32 channels as 8
+        // float4 quads at a pitch of 9 slots (conflict-free channel-major reads, 2-way conflicts on the position-major writes)
         const int py0 = half == 0 ? 1 : 0, py1 = 1 - py0;
         float4* const zt4 = reinterpret_cast<float4*>(zt);
-        float4* const zw0 = zt4 + (((2 * r + py0) * 2 + half) * 16 + c) * 8;
-        float4* const zw1 = zt4 + (((2 * r + py1) * 2 + half) * 16 + c) * 8;
-        const int wsw = c & 7;
-        // blur role: thread = 4 channels (quad q4) of one output column ox, walking the 15 z rows of the tile
+        float4* const zw0 = zt4 + ((2 * r + py0) * 32 + 2 * c + half) * U2_ZT_PITCH;
+        float4* const zw1 = zt4 + ((2 * r + py1) * 32 + 2 * c + half) * U2_ZT_PITCH;
+        // blur role: thread = 4 channels (quad q4) of one output column ox, walking the 15 z rows of the tile top to bottom;
+        // output (oy, ox) reads z rows oy+1 .. oy+4 and z columns ox+1 .. ox+4
         const int q4 = e & 7, ox = e >> 3;
         const bool blur_active = ox < U2_OWN_X;
-        const float4* zr[4];                    // the four z columns ox + 1 + b of z row 1
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int X = ox + 1 + b, cc = X >> 1;
-            zr[b] = zt4 + 256 + (((X & 1) * 16 + cc) * 8 + (q4 ^ (cc & 7)));
-        }
+        const float4* const zrd = zt4 + (32 + ox + 1) * U2_ZT_PITCH + q4;       // z row 1, column ox+1
         const float fx0 = P.fx[0], fx1 = P.fx[1], fx2 = P.fx[2], fx3 = P.fx[3];
         const float fy0 = P.fy[0], fy1 = P.fy[1], fy2 = P.fy[2], fy3 = P.fy[3];
         // pointwise parameters, normalised once: lrelu(u) * gain == lrelu(u * gain) for gain > 0, so the gain is folded into
@@ -267,16 +300,18 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
         const int row_elems = P.OW * P.Co;      // elements between vertically adjacent pixels (tensor sizes are < 2^31)
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x, ++tile_iter) {
             int m = tile / P.nblk;
             const int nb = tile - m * P.nblk;
             const int kx = m % P.tiles_x;
             m /= P.tiles_x;
             const int ky = m % P.tiles_y;
             const int n = m / P.tiles_y;
+            if (e == 0) *epi_progress = tile_iter;
 
             float accv[128];
-            for (int ks = 0; ks < kslabs; ++ks) {
+            for (int ks = 0; ks < kslabs; ks += P.chunk_slabs) {
                 mbar_wait(&t_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + half * 128);
@@ -311,8 +346,8 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
 #pragma unroll
                 for (int qq = 0; qq < 8; ++qq) {
                     const int i0 = g * 32 + qq * 4;
-                    zw0[qq ^ wsw] = make_float4(accv[i0], accv[i0 + 1], accv[i0 + 2], accv[i0 + 3]);
-                    zw1[qq ^ wsw] = make_float4(accv[64 + i0], accv[64 + i0 + 1], accv[64 + i0 + 2], accv[64 + i0 + 3]);
+                    zw0[qq] = make_float4(accv[i0], accv[i0 + 1], accv[i0 + 2], accv[i0 + 3]);
+                    zw1[qq] = make_float4(accv[64 + i0], accv[64 + i0 + 1], accv[64 + i0 + 2], accv[64 + i0 + 3]);
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(U2_EPI_THREADS) : "memory");
                 if (!col_valid) continue;
@@ -321,63 +356,81 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                 const float4 sd = *reinterpret_cast<const float4*>(stg + lc);
                 const float4 sb = *reinterpret_cast<const float4*>(stg + 64 + lc);
                 const float4 sn = *reinterpret_cast<const float4*>(stg + 128 + lc);
-                // element index of (n, y0, x, first channel); rows advance by row_elems
-                const int e0 = ((n * P.OH + y0) * P.OW + x) * P.Co + nb * 64 + lc;
-                const __half* p_sh = epi.skip_hi + e0;
-                const __half* p_sl = epi.skip_lo + e0;
-                __half* p_oh = epi.out_hi + e0;
-                __half* p_ol = epi.out_lo + e0;
-                float* p_of = epi.out_f32 + e0;
+                // element index of (n, y0, x, first channel); one output row further = + row_elems
+                int eo = ((n * P.OH + y0) * P.OW + x) * P.Co + nb * 64 + lc;
                 const float* p_nz = epi.noise + ((long long)n * epi.noise_sn + (long long)y0 * P.OW + x);
 
-                // skip planes / noise of output row i: fetched at step t = i, consumed at t = i + 3
-                uint2 skh[12], skl[12];
-                float nz[12];
-                float4 h[4];
+                // horizontal 4-tap pass of one z row
+                auto hrow = [&](const float4* zp) -> float4 {
+                    const float4 l0 = zp[0], l1 = zp[U2_ZT_PITCH], l2 = zp[2 * U2_ZT_PITCH], l3 = zp[3 * U2_ZT_PITCH];
+                    return f4_fma(fx3, l3, f4_fma(fx2, l2, f4_fma(fx1, l1, f4_mul(fx0, l0))));
+                };
+                // the skip planes and the noise are fetched one block of 4 output rows ahead (raw values; nothing waits on them
+                // before the block that consumes them)
+                uint2 ch_[4], cl_[4], nh_[4], nl_[4];
+                float cn_[4], nn_[4];
+                auto prefetch = [&](int i0, int eoff, uint2* sh, uint2* sl, float* sz) {
 #pragma unroll
-                for (int t = 0; t < 15; ++t) {
-                    if (t < 12) {
-                        skh[t] = make_uint2(0u, 0u); skl[t] = make_uint2(0u, 0u); nz[t] = 0.f;
-                        if (t < rows_valid) {
+                    for (int j = 0; j < 4; ++j) {
+                        sh[j] = make_uint2(0u, 0u); sl[j] = make_uint2(0u, 0u); sz[j] = 0.f;
+                        if (i0 + j < rows_valid) {
                             if (has_skip) {
-                                skh[t] = __ldg(reinterpret_cast<const uint2*>(p_sh + t * row_elems));
-                                skl[t] = __ldg(reinterpret_cast<const uint2*>(p_sl + t * row_elems));
+                                sh[j] = __ldg(reinterpret_cast<const uint2*>(epi.skip_hi + eoff + j * row_elems));
+                                sl[j] = __ldg(reinterpret_cast<const uint2*>(epi.skip_lo + eoff + j * row_elems));
                             }
-                            if (has_noise) nz[t] = __ldg(p_nz + t * P.OW) * nstr;
+                            if (has_noise) sz[j] = __ldg(p_nz + (i0 + j) * P.OW);
                         }
                     }
-                    const float4 l0 = zr[0][t * 256], l1 = zr[1][t * 256], l2 = zr[2][t * 256], l3 = zr[3][t * 256];
-                    h[t & 3] = f4_fma(fx3, l3, f4_fma(fx2, l2, f4_fma(fx1, l1, f4_mul(fx0, l0))));
-                    if (t >= 3) {
-                        const int i = t - 3;
-                        if (i < rows_valid) {
-                            const float4 o = f4_fma(fy3, h[t & 3], f4_fma(fy2, h[(t - 1) & 3], f4_fma(fy1, h[(t - 2) & 3], f4_mul(fy0, h[(t - 3) & 3]))));
-                            float v0 = fmaf(o.x, sd.x, nz[i]) + sb.x, v1 = fmaf(o.y, sd.y, nz[i]) + sb.y;
-                            float v2 = fmaf(o.z, sd.z, nz[i]) + sb.z, v3 = fmaf(o.w, sd.w, nz[i]) + sb.w;
+                };
+                prefetch(0, eo, ch_, cl_, cn_);
+                const float4* zp = zrd;
+                float4 h0 = hrow(zp), h1 = hrow(zp + U2_ZT_ROW), h2 = hrow(zp + 2 * U2_ZT_ROW), h3;
+                zp += 3 * U2_ZT_ROW;
+#pragma unroll 1
+                for (int blk = 0; blk < 3; ++blk) {
+                    if (blk < 2) prefetch(4 * blk + 4, eo + 4 * row_elems, nh_, nl_, nn_);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // ring of the last four horizontal rows, rotated statically over the 4 unrolled steps
+                        float4& ha = j == 0 ? h0 : (j == 1 ? h1 : (j == 2 ? h2 : h3));
+                        float4& hb = j == 0 ? h1 : (j == 1 ? h2 : (j == 2 ? h3 : h0));
+                        float4& hc = j == 0 ? h2 : (j == 1 ? h3 : (j == 2 ? h0 : h1));
+                        float4& hd = j == 0 ? h3 : (j == 1 ? h0 : (j == 2 ? h1 : h2));
+                        hd = hrow(zp + j * U2_ZT_ROW);
+                        if (4 * blk + j < rows_valid) {
+                            const float4 o = f4_fma(fy3, hd, f4_fma(fy2, hc, f4_fma(fy1, hb, f4_mul(fy0, ha))));
+                            const float nzs = cn_[j] * nstr;
+                            float v0 = fmaf(o.x, sd.x, nzs) + sb.x, v1 = fmaf(o.y, sd.y, nzs) + sb.y;
+                            float v2 = fmaf(o.z, sd.z, nzs) + sb.z, v3 = fmaf(o.w, sd.w, nzs) + sb.w;
                             v0 = fminf(fmaxf(fmaxf(v0, v0 * alpha_e), -clamp_e), clamp_e);
                             v1 = fminf(fmaxf(fmaxf(v1, v1 * alpha_e), -clamp_e), clamp_e);
                             v2 = fminf(fmaxf(fmaxf(v2, v2 * alpha_e), -clamp_e), clamp_e);
                             v3 = fminf(fmaxf(fmaxf(v3, v3 * alpha_e), -clamp_e), clamp_e);
                             {
-                                const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&skh[i].x));
-                                const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&skh[i].y));
-                                const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&skl[i].x));
-                                const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&skl[i].y));
+                                const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&ch_[j].x));
+                                const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&ch_[j].y));
+                                const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&cl_[j].x));
+                                const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&cl_[j].y));
                                 v0 += a0.x + b0.x; v1 += a0.y + b0.y; v2 += a1.x + b1.x; v3 += a1.y + b1.y;
                             }
-                            if (has_f32) *reinterpret_cast<float4*>(p_of + i * row_elems) = make_float4(v0, v1, v2, v3);
+                            const int eoj = eo + j * row_elems;
+                            if (has_f32) *reinterpret_cast<float4*>(epi.out_f32 + eoj) = make_float4(v0, v1, v2, v3);
                             if (has_planes) {
                                 v0 *= sn.x; v1 *= sn.y; v2 *= sn.z; v3 *= sn.w;
                                 const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
                                 const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                                 const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
-                                *reinterpret_cast<uint2*>(p_oh + i * row_elems) =
+                                *reinterpret_cast<uint2*>(epi.out_hi + eoj) =
                                     make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-                                *reinterpret_cast<uint2*>(p_ol + i * row_elems) =
+                                *reinterpret_cast<uint2*>(epi.out_lo + eoj) =
                                     make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
                             }
                         }
                     }
+                    zp += 4 * U2_ZT_ROW;
+                    eo += 4 * row_elems;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { ch_[j] = nh_[j]; cl_[j] = nl_[j]; cn_[j] = nn_[j]; }
                 }
             }
         }
@@ -420,6 +473,7 @@ extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
     for (int i = 0; i < 4; ++i) { P.fx[i] = d->fx[i]; P.fy[i] = d->fy[i] * d->gain; }
     P.acc_comp = d->acc_comp == 0.f ? SHGAN_ACC_COMP_DEFAULT : (d->acc_comp < 0.f ? 0.f : d->acc_comp);
     P.passes = d->passes == 0 ? 3 : d->passes;
+    P.chunk_slabs = (d->C / 64) % 2 == 0 && d->C >= 256 ? 2 : 1;
     for (int sg = 0; sg < 4; ++sg) {
         P.sg_idesc[sg] = (1u << 4) | ((uint32_t)(u2_n(sg) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         P.sg_col[sg] = (uint32_t)u2_col(sg);
