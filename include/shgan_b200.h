@@ -239,15 +239,19 @@ int shgan_style_prep_batched(const float* raw, int64_t raw_stride, int N, const 
 
 /* ---- Spectral Hint Unit ----------------------------------------------------------------------
  * replaces SHU.forward, lib/model_zoo/shgan.py:312-336 (cuFFT rfftn/irfftn + ~340 ATen calls).
- * x [N,C,R,R] fp32 NCHW (R = input_res, power of two, 8..128; C*2 <= 64)
+ * x [N,C,R,R] fp32 NCHW (R = input_res, power of two, 4..512; C*2 <= 64)
  * conv0_w [2C,2C], conv0_b [2C], df1_w [2C, 2C*6] (reference parameter layouts),
  * cw [6,R,R/2+1] and the Gaussian band masks gauss[r] ([r, r/2+1], r = lowest_res..R, concatenated
  * lowest band first) are the constants of shgan.py:70-121,280-310.
+ * packed_w: the fp16 hi/lo operands of the tensor-core channel mix (C == 32), written ONCE per parameter set by
+ *   shgan_shu_pack into a buffer of shgan_shu_packed_bytes(C) bytes; NULL = pack into the workspace on every call.
  * spec_ws: workspace of shgan_shu_workspace_bytes(N,C,R) bytes.
  * outs[k] -> [N,C,r_k,r_k] fp32 for r_k = lowest_res * 2^k. */
+int64_t shgan_shu_packed_bytes(int C);
+int shgan_shu_pack(const float* conv0_w, const float* df1_w, void* packed, int C, void* stream);
 int64_t shgan_shu_workspace_bytes(int N, int C, int R);
 int shgan_shu_fwd(const float* x, const float* conv0_w, const float* conv0_b, const float* df1_w,
-                  const float* cw, const float* gauss, void* spec_ws,
+                  const float* cw, const float* gauss, const void* packed_w, void* spec_ws,
                   float* const* outs, int num_bands, int N, int C, int R, int lowest_res, void* stream);
 
 #ifdef __cplusplus

@@ -89,8 +89,10 @@ SIGNATURES = {
     'shgan_normalize_2nd_moment': (i32, [fp, fp, i32, i32, vp]),
     'shgan_style_prep': (i32, [fp, fp, fp, fp, i32, i32, i32, i32, f32, vp]),
     'shgan_style_prep_batched': (i32, [fp, i64, i32, C.POINTER(StyleBatch), vp]),
+    'shgan_shu_packed_bytes': (i64, [i32]),
+    'shgan_shu_pack': (i32, [fp, fp, vp, i32, vp]),
     'shgan_shu_workspace_bytes': (i64, [i32, i32, i32]),
-    'shgan_shu_fwd': (i32, [fp, fp, fp, fp, fp, fp, vp, C.POINTER(fp), i32, i32, i32, i32, i32, vp]),
+    'shgan_shu_fwd': (i32, [fp, fp, fp, fp, fp, fp, vp, vp, C.POINTER(fp), i32, i32, i32, i32, i32, vp]),
 }
 
 _lib = None

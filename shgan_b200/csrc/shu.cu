@@ -2,23 +2,24 @@
 // (torch.fft.rfftn -> row shift -> cat(re,im) -> conv0 1x1 + bias + ReLU -> heterogeneous_filter (:143-160)
 // -> complex -> per band: crop, Gaussian mask, un-shift, torch.fft.irfftn).
 //
-// Three kernels, all spectra stay in shared memory / registers inside a kernel:
+// Three launches for input_res <= 128 (the released model: 64), spectra in shared memory / registers inside each:
 //   1. shu_rfft2_kernel   one CTA per (n,c) plane: radix-2 shared-memory FFT, two real rows packed into one
 //                         complex transform, columns transformed in place, 1/(R*R) scaling ('forward' norm) and
 //                         the DC-to-centre row shift folded into the store.  -> spec1 [N, 2C, R, R/2+1] (re | im)
-//   2. channel mixing.  C == 32 (the released model): on the tensor cores -- the spectrum is re-laid as NHWC hi/lo planes
-//                         (x R so that the 'forward'-normalised values sit in fp16's normal range) and the two 1x1
-//                         convolutions run through the tcgen05 igemm (conv_tc.cu) with its fp32-class 3-pass scheme:
-//                         conv0 + bias + ReLU as a 1-tap conv, the heterogeneous filter as a 6-"tap" conv whose taps all
-//                         read the same pixel, use the 6 anchor filters df1[:, o*6+k] as weights and are blended per
-//                         frequency bin by cw[k,bin] in the register-level accumulation (ConvGeom::chunk_scale).
-//                         Any other C: shu_mix_kernel, per-frequency-bin fp32 FMA mixing for a tile of 32 bins: conv0 (2C x 2C) + bias + ReLU,
-//                         then the heterogeneous filter out[o] = sum_k cw[k,bin] * sum_i t[i] * df1[i, o*6+k]
-//                         with all weights resident in shared memory (broadcast 128-bit reads, 4 FMA per LDS).
+//   2. channel mixing, ONE kernel.  C == 32 (the released model): shu_mix_mma_kernel -- per tile of 64 frequency bins the
+//                         64 spectrum channels are split into fp16 hi/lo in shared memory and both 1x1 convolutions run
+//                         on the tensor cores (warp-level mma.sync m16n8k16, hi*hi + lo*hi + hi*lo, fp32 accumulators in
+//                         registers): conv0 + bias + ReLU, whose result never leaves shared memory, then the six anchor
+//                         filters df1[:, o*6+k] blended per bin by cw[k,bin] in registers (heterogeneous filter).  The
+//                         packed fp16 weights are prepared ONCE by shgan_shu_pack (engine.refresh), not per forward.
+//                         Any other C: shu_mix_kernel, per-bin fp32 FMA mixing with the weights in shared memory.
 //                         -> spec2 [N, 2C, R, R/2+1]
 //   3. shu_irfft2_kernel  one CTA per (n,c,band): crop + Gaussian band mask + un-shift folded into the load,
 //                         inverse column FFTs, Hermitian extension with the DC/Nyquist imaginary parts dropped
 //                         (C2R semantics of pocketfft/cuFFT on non-Hermitian input), two rows per complex FFT.
+// input_res 256 / 512 (BASELINE.json config C5 sweeps the unit up to 512): a plane no longer fits one SM's shared memory;
+// the transforms then run as a row pass and a column pass through a float2 scratch in global memory
+// (shu_fft_rows_kernel / shu_fft_cols_kernel and their inverses), same arithmetic, five launches more.
 #include "conv_common.cuh"
 
 namespace shgan {
@@ -188,6 +189,7 @@ shu_irfft2_kernel(const float* __restrict__ spec2, const float* __restrict__ gau
     const int band = blockIdx.y;
     const int log2r = bands.lowest_log2 + band;
     const int r = 1 << log2r, rh = r / 2 + 1, Rh = R / 2 + 1;
+    if (r > 128) return;      // large bands run as a column pass + a row pass through global memory
     float2* colbuf = sm;
     float2* rowbuf = colbuf + r * rh;
     float2* tw = rowbuf + (r / 2) * r;
@@ -227,59 +229,273 @@ shu_irfft2_kernel(const float* __restrict__ spec2, const float* __restrict__ gau
     }
 }
 
-// ---- 2b. operand packing for the tensor-core mix (C == 32) -------------------------------------
-// w0 hi/lo [64][64] = conv0.weight [o][i]; w1 hi/lo [6][64][64]: w1[k][o][i] = df1[i][o*6+k]; sc [N*64] = `scale`
+// ---- 1b / 3b. transforms through global memory for input_res (or band size) > 128 ------------------------------
+constexpr int BIG_RP = 8;     // row pairs per CTA in the row passes
+constexpr int BIG_CB = 8;     // columns per CTA in the column passes
+
+// forward row pass: grid (N*C, R/2/BIG_RP); smem [BIG_RP][R] + tw[R/2] float2.  tmp[plane][row][k], k < Rh (natural order)
 __global__ void __launch_bounds__(256)
-shu_pack_kernel(const float* __restrict__ conv0_w, const float* __restrict__ df1_w, __half* w0_hi, __half* w0_lo, __half* w1_hi,
-                __half* w1_lo, float* sc, int n_sc, float scale) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (int i = gid; i < 64 * 64; i += stride) split_f32(__ldg(conv0_w + i), w0_hi[i], w0_lo[i]);
-    for (int i = gid; i < 6 * 64 * 64; i += stride) {
-        const int k = i / 4096, o = (i >> 6) & 63, ii = i & 63;
-        split_f32(__ldg(df1_w + ii * 384 + o * 6 + k), w1_hi[i], w1_lo[i]);
+shu_fft_rows_kernel(const float* __restrict__ x, float2* __restrict__ tmp, int R, int log2R) {
+    extern __shared__ float2 sm[];
+    const int Rh = R / 2 + 1;
+    float2* rowbuf = sm;
+    float2* tw = rowbuf + BIG_RP * R;
+    const float* xp = x + (long long)blockIdx.x * R * R;
+    const int p0 = blockIdx.y * BIG_RP;
+    fill_twiddles(tw, R);
+    for (int i = threadIdx.x; i < BIG_RP * R; i += blockDim.x) {
+        const int pp = i / R, xx = i - pp * R;
+        rowbuf[pp * R + brev(xx, log2R)] = make_float2(__ldg(xp + (long long)(2 * (p0 + pp)) * R + xx), __ldg(xp + (long long)(2 * (p0 + pp) + 1) * R + xx));
     }
-    for (int i = gid; i < n_sc; i += stride) sc[i] = scale;
+    __syncthreads();
+    fft_smem(rowbuf, log2R, BIG_RP, 1, R, -1.f, tw, log2R);
+    float2* tp = tmp + (long long)blockIdx.x * R * Rh;
+    for (int i = threadIdx.x; i < BIG_RP * Rh; i += blockDim.x) {
+        const int pp = i / Rh, k = i - pp * Rh;
+        const float2 z = rowbuf[pp * R + k], zz = rowbuf[pp * R + ((R - k) & (R - 1))];
+        tp[(long long)(2 * (p0 + pp)) * Rh + k] = make_float2(0.5f * (z.x + zz.x), 0.5f * (z.y - zz.y));
+        tp[(long long)(2 * (p0 + pp) + 1) * Rh + k] = make_float2(0.5f * (z.y + zz.y), -0.5f * (z.x - zz.x));
+    }
 }
 
-static int shu_mix_tensor(const float* spec1, float* spec2, const float* conv0_w, const float* conv0_b, const float* df1_w,
-                          const float* cw, uint8_t* ws, int N, int R, cudaStream_t stream) {
+// forward column pass: grid (N*C, ceil(Rh/BIG_CB)); smem [R][BIG_CB] + tw.  Writes spec1 (scaled, rows shifted) like shu_rfft2_kernel
+__global__ void __launch_bounds__(256)
+shu_fft_cols_kernel(const float2* __restrict__ tmp, float* __restrict__ spec1, int C, int R, int log2R) {
+    extern __shared__ float2 sm[];
     const int Rh = R / 2 + 1;
-    const long long px = (long long)N * R * Rh;
-    // workspace: P1 hi | P1 lo | P2 hi | P2 lo (fp16 [N,R,Rh,64]) | Y fp32 [N,R,Rh,64] | w0 hi/lo | w1 hi/lo | sc [N*64]
-    __half* p1_hi = (__half*)ws;
-    __half* p1_lo = p1_hi + px * 64;
-    __half* p2_hi = p1_lo + px * 64;
-    __half* p2_lo = p2_hi + px * 64;
-    float* y = (float*)(p2_lo + px * 64);
-    __half* w0_hi = (__half*)(y + px * 64);
-    __half* w0_lo = w0_hi + 4096;
-    __half* w1_hi = w0_lo + 4096;
-    __half* w1_lo = w1_hi + 6 * 4096;
-    float* sc = (float*)(w1_lo + 6 * 4096);
-    const float scale = (float)R;      // |X_forward-normalised| <= max|x| <= 256 (lrelu_agc clamp): x R stays below fp16 max
-    shu_pack_kernel<<<32, 256, 0, stream>>>(conv0_w, df1_w, w0_hi, w0_lo, w1_hi, w1_lo, sc, N * 64, scale);
-    SHGAN_LAUNCH_CHECK();
-    if (int e = shgan_nchw_to_planes(spec1, nullptr, nullptr, sc, p1_hi, p1_lo, N, 64, R, Rh, 0, 64, stream)) return e;
+    float2* colbuf = sm;
+    float2* tw = colbuf + R * BIG_CB;
+    const int n = blockIdx.x / C, c = blockIdx.x % C, k0 = blockIdx.y * BIG_CB;
+    const float2* tp = tmp + (long long)blockIdx.x * R * Rh;
+    fill_twiddles(tw, R);
+    for (int i = threadIdx.x; i < R * BIG_CB; i += blockDim.x) {
+        const int j = i / BIG_CB, kk = i - j * BIG_CB;
+        colbuf[brev(j, log2R) * BIG_CB + kk] = k0 + kk < Rh ? tp[(long long)j * Rh + k0 + kk] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    fft_smem(colbuf, log2R, BIG_CB, BIG_CB, 1, -1.f, tw, log2R);
+    const float sc = 1.f / ((float)R * (float)R);
+    float* re = spec1 + ((long long)n * 2 * C + c) * R * Rh;
+    float* im = spec1 + ((long long)n * 2 * C + C + c) * R * Rh;
+    for (int i = threadIdx.x; i < R * BIG_CB; i += blockDim.x) {
+        const int j = i / BIG_CB, kk = i - j * BIG_CB;
+        if (k0 + kk < Rh) {
+            const float2 v = colbuf[((j + R / 2 + 1) & (R - 1)) * BIG_CB + kk];
+            re[(long long)j * Rh + k0 + kk] = v.x * sc;
+            im[(long long)j * Rh + k0 + kk] = v.y * sc;
+        }
+    }
+}
 
-    ConvGeom g{};
-    g.num_src = 1; g.src_hi[0] = p1_hi; g.src_lo[0] = p1_lo; g.src_h[0] = R; g.src_w[0] = Rh;
-    g.N = N; g.C = 64; g.Co = 64; g.w_hi = w0_hi; g.w_lo = w0_lo;
-    g.ntaps = 1; g.tap_src[0] = 0; g.tap_dy[0] = 0; g.tap_dx[0] = 0; g.tap_w[0] = 0;
-    g.OH = R; g.OW = Rh; g.mode = 0; g.chunk_scale = nullptr; g.acc_comp = SHGAN_ACC_COMP_DEFAULT;
-    EpiParams e0{};
-    e0.wgain = 1.f / scale; e0.bias = conv0_b; e0.act = 1; e0.act_alpha = 0.f; e0.act_gain = 1.f; e0.act_clamp = -1.f;   // ReLU
-    e0.next_scale = sc;                                                                                                  // x R again
-    e0.out_hi = p2_hi; e0.out_lo = p2_lo;
-    if (int e = launch_conv_tc(g, e0, 0, 3, stream)) return e;
+// inverse column pass of one band of size r: grid (N*C, ceil(rh/BIG_CB)); crop + mask + un-shift folded into the load
+__global__ void __launch_bounds__(256)
+shu_ifft_cols_kernel(const float* __restrict__ spec2, const float* __restrict__ gm, float2* __restrict__ tmp, int C, int R, int r, int log2r) {
+    extern __shared__ float2 sm[];
+    const int rh = r / 2 + 1, Rh = R / 2 + 1;
+    float2* colbuf = sm;
+    float2* tw = colbuf + r * BIG_CB;
+    const int n = blockIdx.x / C, c = blockIdx.x % C, k0 = blockIdx.y * BIG_CB;
+    const float* re = spec2 + ((long long)n * 2 * C + c) * R * Rh;
+    const float* im = spec2 + ((long long)n * 2 * C + C + c) * R * Rh;
+    fill_twiddles(tw, r);
+    for (int i = threadIdx.x; i < r * BIG_CB; i += blockDim.x) {
+        const int j = i / BIG_CB, kk = i - j * BIG_CB, k = k0 + kk;
+        float2 v = make_float2(0.f, 0.f);
+        if (k < rh) {
+            const int cj = (j + r / 2 - 1) & (r - 1);
+            const long long src = (long long)(R / 2 - r / 2 + cj) * Rh + k;
+            const float gq = __ldg(gm + (long long)cj * rh + k);
+            v = make_float2(__ldg(re + src) * gq, __ldg(im + src) * gq);
+        }
+        colbuf[brev(j, log2r) * BIG_CB + kk] = v;
+    }
+    __syncthreads();
+    fft_smem(colbuf, log2r, BIG_CB, BIG_CB, 1, +1.f, tw, log2r);
+    float2* tp = tmp + (long long)blockIdx.x * r * rh;
+    for (int i = threadIdx.x; i < r * BIG_CB; i += blockDim.x) {
+        const int j = i / BIG_CB, kk = i - j * BIG_CB;
+        if (k0 + kk < rh) tp[(long long)j * rh + k0 + kk] = colbuf[j * BIG_CB + kk];
+    }
+}
 
-    g.src_hi[0] = p2_hi; g.src_lo[0] = p2_lo; g.w_hi = w1_hi; g.w_lo = w1_lo;
-    g.ntaps = 6;
-    for (int k = 0; k < 6; ++k) { g.tap_src[k] = 0; g.tap_dy[k] = 0; g.tap_dx[k] = 0; g.tap_w[k] = k; }
-    g.chunk_scale = cw;                 // [6][R*Rh]
-    EpiParams e1{};
-    e1.wgain = 1.f / scale; e1.act = 0; e1.act_gain = 1.f; e1.act_clamp = -1.f; e1.out_f32 = y;
-    if (int e = launch_conv_tc(g, e1, 0, 3, stream)) return e;
-    return shgan_nhwc_to_nchw_f32(y, spec2, N, 64, R, Rh, stream);
+// inverse row pass: grid (N*C, r/2/BIG_RP); Hermitian extension, two rows per complex transform
+__global__ void __launch_bounds__(256)
+shu_ifft_rows_kernel(const float2* __restrict__ tmp, float* __restrict__ out, int r, int log2r) {
+    extern __shared__ float2 sm[];
+    const int rh = r / 2 + 1;
+    float2* rowbuf = sm;
+    float2* tw = rowbuf + BIG_RP * r;
+    const float2* tp = tmp + (long long)blockIdx.x * r * rh;
+    const int p0 = blockIdx.y * BIG_RP;
+    fill_twiddles(tw, r);
+    for (int i = threadIdx.x; i < BIG_RP * r; i += blockDim.x) {
+        const int pp = i / r, k = i - pp * r;
+        const int kk = k <= r / 2 ? k : r - k;
+        float2 ya = tp[(long long)(2 * (p0 + pp)) * rh + kk], yb = tp[(long long)(2 * (p0 + pp) + 1) * rh + kk];
+        if (k > r / 2) { ya.y = -ya.y; yb.y = -yb.y; }
+        if (k == 0 || k == r / 2) { ya.y = 0.f; yb.y = 0.f; }
+        rowbuf[pp * r + brev(k, log2r)] = make_float2(ya.x - yb.y, ya.y + yb.x);
+    }
+    __syncthreads();
+    fft_smem(rowbuf, log2r, BIG_RP, 1, r, +1.f, tw, log2r);
+    float* op = out + (long long)blockIdx.x * r * r;
+    for (int i = threadIdx.x; i < BIG_RP * 2 * r; i += blockDim.x) {
+        const int jj = i / r, xx = i - jj * r;          // jj: local output row 0 .. 2*BIG_RP-1
+        const float2 v = rowbuf[(jj >> 1) * r + xx];
+        op[(long long)(2 * p0 + jj) * r + xx] = (jj & 1) ? v.y : v.x;
+    }
+}
+
+// ---- 2b. tensor-core channel mix for C == 32 (64 spectrum channels) ---------------------------------
+// Packed weights (shgan_shu_pack, once per parameter set): 7 matrices [64 out][64 in] as fp16 hi and lo planes, rows padded to
+// 72 halves (144 B: conflict-free ldmatrix): matrix 0 = conv0.weight[o][i]; matrix 1+k = W1_k[o2][o] = df1[o][o2*6+k].
+constexpr int MM_LD = 72;                          // smem / packed row pitch in halves
+constexpr int MM_MAT = 64 * MM_LD;                 // halves per matrix plane
+constexpr int MM_TB = 64;                          // frequency bins per tile
+constexpr int MM_W_HALVES = 7 * 2 * MM_MAT;        // all packed weights
+constexpr int MM_SMEM_BYTES = (MM_W_HALVES + 4 * MM_MAT) * 2 + (64 + 6 * MM_TB) * 4;   // weights | X hi/lo | T hi/lo | bias | cw tile
+
+__global__ void __launch_bounds__(256)
+shu_pack_kernel(const float* __restrict__ conv0_w, const float* __restrict__ df1_w, __half* __restrict__ packed) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int i = gid; i < 7 * 64 * MM_LD; i += stride) {
+        const int m = i / MM_MAT, r = (i / MM_LD) % 64, c = i % MM_LD;
+        float v = 0.f;
+        if (c < 64) v = m == 0 ? __ldg(conv0_w + r * 64 + c) : __ldg(df1_w + c * 384 + r * 6 + (m - 1));
+        __half h, l;
+        split_f32(v, h, l);
+        packed[(m * 2) * MM_MAT + r * MM_LD + c] = h;
+        packed[(m * 2 + 1) * MM_MAT + r * MM_LD + c] = l;
+    }
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const __half* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __half* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// acc[nt][4] (+)= W[mt*16 .. +16][0..64) * B[0..64)[nh*32 + nt*8 .. +8), three split-precision passes.
+// W hi/lo: [64][MM_LD] row-major (A operand); B hi/lo: [64 k][MM_LD] with the bins contiguous (B operand via ldmatrix.trans)
+__device__ __forceinline__ void mix_gemm(float acc[4][4], const __half* w_hi, const __half* w_lo, const __half* b_hi,
+                                         const __half* b_lo, int mt, int nh, int lane) {
+    const int lrow = lane & 15, lcol = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ah[4], al[4];
+        ldsm_x4(ah, w_hi + (mt * 16 + lrow) * MM_LD + ks * 16 + lcol);
+        ldsm_x4(al, w_lo + (mt * 16 + lrow) * MM_LD + ks * 16 + lcol);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            uint32_t bh[4], bl[4];
+            ldsm_x4_trans(bh, b_hi + (ks * 16 + lrow) * MM_LD + nh * 32 + np * 16 + lcol);
+            ldsm_x4_trans(bl, b_lo + (ks * 16 + lrow) * MM_LD + nh * 32 + np * 16 + lcol);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float* d = acc[np * 2 + j];
+                mma_16816(d, ah, bh[2 * j], bh[2 * j + 1]);
+                mma_16816(d, al, bh[2 * j], bh[2 * j + 1]);
+                mma_16816(d, ah, bl[2 * j], bl[2 * j + 1]);
+            }
+        }
+    }
+}
+
+// persistent grid over tiles (n, 64 bins); 256 threads = 8 warps: warp w owns output channels (w & 3) * 16 .. +16 and bins
+// (w >> 2) * 32 .. +32 of the tile
+__global__ void __launch_bounds__(256, 1)
+shu_mix_mma_kernel(const float* __restrict__ spec1, const __half* __restrict__ packed, const float* __restrict__ conv0_b,
+                   const float* __restrict__ cw, float* __restrict__ spec2, int N, int bins, float scale) {
+    extern __shared__ __align__(16) uint8_t smm[];
+    __half* w_s = reinterpret_cast<__half*>(smm);                 // [7][2][64][MM_LD]
+    __half* x_hi = w_s + MM_W_HALVES;
+    __half* x_lo = x_hi + MM_MAT;
+    __half* t_hi = x_lo + MM_MAT;
+    __half* t_lo = t_hi + MM_MAT;
+    float* b_s = reinterpret_cast<float*>(t_lo + MM_MAT);         // [64]
+    float* cw_s = b_s + 64;                                       // [6][MM_TB]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = warp & 3, nh = warp >> 2, g = lane >> 2, t4 = lane & 3;
+    for (int i = threadIdx.x; i < MM_W_HALVES / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(packed) + i);
+    if (threadIdx.x < 64) b_s[threadIdx.x] = __ldg(conv0_b + threadIdx.x);
+    const int tiles_per_n = (bins + MM_TB - 1) / MM_TB;
+    const float inv_scale = 1.f / scale;
+    for (int tile = blockIdx.x; tile < N * tiles_per_n; tile += gridDim.x) {
+        const int n = tile / tiles_per_n, bin0 = (tile - n * tiles_per_n) * MM_TB;
+        __syncthreads();                                          // previous tile's readers of X / cw are done (and the weights are in)
+        // X tile: 64 channels x 64 bins, x scale (the 'forward'-normalised spectrum is tiny: keep it in fp16's normal range)
+        for (int i = threadIdx.x; i < 64 * MM_TB; i += blockDim.x) {
+            const int ch = i >> 6, b = i & 63;
+            const float v = bin0 + b < bins ? __ldg(spec1 + ((long long)n * 64 + ch) * bins + bin0 + b) * scale : 0.f;
+            __half h, l;
+            split_f32(v, h, l);
+            x_hi[ch * MM_LD + b] = h;
+            x_lo[ch * MM_LD + b] = l;
+        }
+        for (int i = threadIdx.x; i < 6 * MM_TB; i += blockDim.x) {
+            const int k = i >> 6, b = i & 63;
+            cw_s[i] = bin0 + b < bins ? __ldg(cw + (long long)k * bins + bin0 + b) : 0.f;
+        }
+        __syncthreads();
+        // conv0 (1x1) + bias + ReLU (shgan.py:319-321) -> T, kept in shared memory as the next GEMM's B operand (x scale again)
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        mix_gemm(acc, w_s, w_s + MM_MAT, x_hi, x_lo, mt, nh, lane);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int o = mt * 16 + g + hh * 8, b = nh * 32 + nt * 8 + 2 * t4;
+                const float bo = b_s[o];
+                const float v0 = fmaxf(fmaf(acc[nt][2 * hh], inv_scale, bo), 0.f) * scale;
+                const float v1 = fmaxf(fmaf(acc[nt][2 * hh + 1], inv_scale, bo), 0.f) * scale;
+                const __half2 h2 = __floats2half2_rn(v0, v1);
+                const float2 f2 = __half22float2(h2);
+                *reinterpret_cast<__half2*>(t_hi + o * MM_LD + b) = h2;
+                *reinterpret_cast<__half2*>(t_lo + o * MM_LD + b) = __floats2half2_rn(v0 - f2.x, v1 - f2.y);
+            }
+        }
+        __syncthreads();
+        // heterogeneous filter (shgan.py:143-160): out = sum_k cw[k,bin] * (W1_k . T)
+        float out[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i][0] = out[i][1] = out[i][2] = out[i][3] = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < 6; ++k) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            const __half* wk = w_s + (1 + k) * 2 * MM_MAT;
+            mix_gemm(acc, wk, wk + MM_MAT, t_hi, t_lo, mt, nh, lane);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float2 c2 = *reinterpret_cast<const float2*>(cw_s + k * MM_TB + nh * 32 + nt * 8 + 2 * t4);
+                out[nt][0] = fmaf(acc[nt][0], c2.x, out[nt][0]); out[nt][1] = fmaf(acc[nt][1], c2.y, out[nt][1]);
+                out[nt][2] = fmaf(acc[nt][2], c2.x, out[nt][2]); out[nt][3] = fmaf(acc[nt][3], c2.y, out[nt][3]);
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int o = mt * 16 + g + hh * 8, b = bin0 + nh * 32 + nt * 8 + 2 * t4;
+                float* dst = spec2 + ((long long)n * 64 + o) * bins + b;
+                if (b + 1 < bins && (bins & 1) == 0) *reinterpret_cast<float2*>(dst) = make_float2(out[nt][2 * hh] * inv_scale, out[nt][2 * hh + 1] * inv_scale);
+                else {
+                    if (b < bins) dst[0] = out[nt][2 * hh] * inv_scale;
+                    if (b + 1 < bins) dst[1] = out[nt][2 * hh + 1] * inv_scale;
+                }
+            }
+        }
+    }
 }
 
 static inline int log2_exact(int v) {
@@ -292,20 +508,31 @@ static inline int log2_exact(int v) {
 
 using namespace shgan;
 
+extern "C" int64_t shgan_shu_packed_bytes(int C) { return C == 32 ? (int64_t)MM_W_HALVES * 2 : 16; }
+
+extern "C" int shgan_shu_pack(const float* conv0_w, const float* df1_w, void* packed, int C, void* stream) {
+    SHGAN_CHECK(conv0_w && df1_w && packed, "null pointer");
+    if (C != 32) return 0;                 // only the tensor-core mix has packed operands
+    shu_pack_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(conv0_w, df1_w, (__half*)packed);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int64_t shgan_shu_workspace_bytes(int N, int C, int R) {
     const int64_t bins = (int64_t)R * (R / 2 + 1);
-    int64_t b = 2LL * N * 2 * C * bins * (int64_t)sizeof(float);                  // spec1, spec2
-    if (C == 32) b += N * bins * 64 * (4 * 2 + 4) + 2 * 7 * 4096 * 2 + (int64_t)N * 64 * 4 + 256;   // tensor-core mix operands
+    int64_t b = 2LL * N * 2 * C * bins * (int64_t)sizeof(float) + 256;            // spec1, spec2
+    if (R > 128) b += (int64_t)N * C * bins * (int64_t)sizeof(float2);            // row/column pass scratch
+    if (C == 32) b += shgan_shu_packed_bytes(C) + 256;                            // on-the-fly weight packing when none is passed
     return b;
 }
 
 extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* conv0_b, const float* df1_w, const float* cw,
-                             const float* gauss, void* spec_ws, float* const* outs, int num_bands, int N, int C, int R,
-                             int lowest_res, void* stream_) {
+                             const float* gauss, const void* packed_w, void* spec_ws, float* const* outs, int num_bands, int N,
+                             int C, int R, int lowest_res, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SHGAN_CHECK(x && conv0_w && conv0_b && df1_w && cw && gauss && spec_ws && outs, "null pointer");
     const int log2R = log2_exact(R), log2low = log2_exact(lowest_res);
-    SHGAN_CHECK(log2R >= 2 && R <= 128, "input_res must be a power of two in 4..128");
+    SHGAN_CHECK(log2R >= 2 && R <= 512, "input_res must be a power of two in 4..512");
     SHGAN_CHECK(log2low >= 1 && lowest_res <= R, "lowest_res must be a power of two in 2..input_res");
     SHGAN_CHECK(num_bands == log2R - log2low + 1 && num_bands <= 8, "num_bands must be log2(input_res/lowest_res)+1");
     SHGAN_CHECK(C >= 4 && C <= 32 && C % 4 == 0, "C must be a multiple of 4 in 4..32");
@@ -314,22 +541,43 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     const int Rh = R / 2 + 1, K2 = 2 * C, bins = R * Rh;
     float* spec1 = (float*)spec_ws;
     float* spec2 = spec1 + (long long)N * K2 * bins;
+    uint8_t* extra = (uint8_t*)(((uintptr_t)(spec2 + (long long)N * K2 * bins) + 255) & ~(uintptr_t)255);
+    float2* tmp = (float2*)extra;                                  // only when R > 128
+    if (R > 128) extra += (long long)N * C * bins * sizeof(float2);
 
     static DeviceInit once;
-    if (int e = device_init(once, nullptr, []() -> int {
+    int num_sms = 148;
+    if (int e = device_init(once, &num_sms, []() -> int {
             SHGAN_CUDA(cudaFuncSetAttribute(shu_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             SHGAN_CUDA(cudaFuncSetAttribute(shu_irfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             SHGAN_CUDA(cudaFuncSetAttribute(shu_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            SHGAN_CUDA(cudaFuncSetAttribute(shu_mix_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
             return 0;
         })) return e;
-    const size_t fft_smem_bytes = ((size_t)(R / 2) * R + (size_t)R * Rh + R / 2) * sizeof(float2);
-    shu_rfft2_kernel<<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, C, R, log2R);
-    SHGAN_LAUNCH_CHECK();
+    const int Rs = R < 128 ? R : 128;       // size the single-CTA transforms see
+    const size_t fft_smem_bytes = ((size_t)(Rs / 2) * Rs + (size_t)Rs * (Rs / 2 + 1) + Rs / 2) * sizeof(float2);
+    if (R <= 128) {
+        shu_rfft2_kernel<<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, C, R, log2R);
+        SHGAN_LAUNCH_CHECK();
+    } else {
+        const size_t sm_rows = ((size_t)BIG_RP * R + R / 2) * sizeof(float2), sm_cols = ((size_t)R * BIG_CB + R / 2) * sizeof(float2);
+        shu_fft_rows_kernel<<<dim3(N * C, R / 2 / BIG_RP), 256, sm_rows, stream>>>(x, tmp, R, log2R);
+        SHGAN_LAUNCH_CHECK();
+        shu_fft_cols_kernel<<<dim3(N * C, ceil_div(Rh, BIG_CB)), 256, sm_cols, stream>>>(tmp, spec1, C, R, log2R);
+        SHGAN_LAUNCH_CHECK();
+    }
 
     if (C == 32) {
-        uint8_t* mix_ws = (uint8_t*)(spec2 + (long long)N * K2 * bins);
-        mix_ws = (uint8_t*)(((uintptr_t)mix_ws + 255) & ~(uintptr_t)255);
-        if (int e = shu_mix_tensor(spec1, spec2, conv0_w, conv0_b, df1_w, cw, mix_ws, N, R, stream)) return e;
+        const __half* packed = (const __half*)packed_w;
+        if (!packed) {                       // op-level callers without a prepared weight set: pack into the workspace
+            if (int e = shgan_shu_pack(conv0_w, df1_w, extra, C, stream)) return e;
+            packed = (const __half*)extra;
+        }
+        const long long tiles = (long long)N * ceil_div(bins, MM_TB);
+        const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+        // |X_forward-normalised| <= max|x| <= 256 (lrelu_agc clamp): x R stays far below fp16 max for R <= 128; larger R use 128
+        shu_mix_mma_kernel<<<grid, 256, MM_SMEM_BYTES, stream>>>(spec1, packed, conv0_b, cw, spec2, N, bins, (float)(R < 128 ? R : 128));
+        SHGAN_LAUNCH_CHECK();
     } else {
         const size_t mix_smem = ((size_t)K2 * K2 + K2 + (size_t)K2 * K2 * 6 + 2 * (size_t)K2 * MIX_TB) * sizeof(float);
         dim3 mgrid(ceil_div(bins, MIX_TB), N);
@@ -348,8 +596,22 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
         bands.gauss_off[k] = off;
         off += r * (r / 2 + 1);
     }
-    dim3 igrid(N * C, num_bands);
-    shu_irfft2_kernel<<<igrid, 256, fft_smem_bytes, stream>>>(spec2, gauss, bands, C, R, log2R);
-    SHGAN_LAUNCH_CHECK();
+    if (lowest_res <= 128) {
+        int small_bands = 0;
+        while (small_bands < num_bands && (lowest_res << small_bands) <= 128) ++small_bands;
+        dim3 igrid(N * C, small_bands);
+        shu_irfft2_kernel<<<igrid, 256, fft_smem_bytes, stream>>>(spec2, gauss, bands, C, R, log2R);
+        SHGAN_LAUNCH_CHECK();
+    }
+    for (int k = 0; k < num_bands; ++k) {
+        const int r = lowest_res << k;
+        if (r <= 128) continue;
+        const int rh = r / 2 + 1, log2r = log2low + k;
+        const size_t sm_rows = ((size_t)BIG_RP * r + r / 2) * sizeof(float2), sm_cols = ((size_t)r * BIG_CB + r / 2) * sizeof(float2);
+        shu_ifft_cols_kernel<<<dim3(N * C, ceil_div(rh, BIG_CB)), 256, sm_cols, stream>>>(spec2, gauss + bands.gauss_off[k], tmp, C, R, r, log2r);
+        SHGAN_LAUNCH_CHECK();
+        shu_ifft_rows_kernel<<<dim3(N * C, r / 2 / BIG_RP), 256, sm_rows, stream>>>(tmp, bands.out[k], r, log2r);
+        SHGAN_LAUNCH_CHECK();
+    }
     return 0;
 }

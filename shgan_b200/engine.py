@@ -143,6 +143,8 @@ class GeneratorEngine:
                 df1_w=shu.df1.weight.detach().contiguous(),
                 cw=P.make_cweight(shu.df1.freedom, (r_in, r_in // 2 + 1)).to(dev).contiguous(),
                 gauss=torch.cat([masks[r].reshape(-1) for r in sorted(masks)]).to(dev).contiguous())
+            # the channel mix's fp16 operands are packed here, once per parameter set, not on every forward
+            self.shu['packed'] = K.shu_pack(self.shu['conv0_w'].float().contiguous(), self.shu['df1_w'].float().contiguous())
 
         # synthesis
         self.syn_res = list(syn.block_res)
@@ -331,7 +333,8 @@ class GeneratorEngine:
         if ws is None:
             ws = torch.empty(K.shu_workspace_bytes(n, ch, rin), dtype=torch.uint8, device=self.dev)
             self._buf[('shu.ws', n)] = ws
-        K.shu_fwd(xin, s['conv0_w'], s['conv0_b'], s['df1_w'], s['cw'], s['gauss'], outs, s['lowest_res'], workspace=ws)
+        K.shu_fwd(xin, s['conv0_w'], s['conv0_b'], s['df1_w'], s['cw'], s['gauss'], outs, s['lowest_res'], workspace=ws,
+                  packed=s['packed'])
         return outs
 
     def styles(self, ws, x_global):

@@ -345,14 +345,26 @@ def shu_workspace_bytes(n, c, r):
 
 
 @_on_tensor_device
-def shu_fwd(x, conv0_w, conv0_b, df1_w, cw, gauss, outs, lowest_res, workspace=None):
-    """x fp32 [N,C,R,R]; outs: list of fp32 [N,C,r,r] for r = lowest_res*2^k; gauss: concatenated band masks."""
+def shu_pack(conv0_w, df1_w):
+    """One-time fp16 hi/lo packing of the SHU weights for the tensor-core channel mix -> uint8 buffer (shgan_shu_pack)."""
+    _f32c(conv0_w, 'conv0_w'); _f32c(df1_w, 'df1_w')
+    c = conv0_w.shape[0] // 2
+    lib = _lib.load()
+    packed = torch.empty(int(lib.shgan_shu_packed_bytes(c)), dtype=torch.uint8, device=conv0_w.device)
+    _lib.check(lib.shgan_shu_pack(_p(conv0_w), _p(df1_w), _p(packed), c, _stream()), 'shgan_shu_pack')
+    return packed
+
+
+@_on_tensor_device
+def shu_fwd(x, conv0_w, conv0_b, df1_w, cw, gauss, outs, lowest_res, workspace=None, packed=None):
+    """x fp32 [N,C,R,R]; outs: list of fp32 [N,C,r,r] for r = lowest_res*2^k; gauss: concatenated band masks;
+    packed: shu_pack(conv0_w, df1_w) (None = pack on every call)."""
     _f32c(x, 'x')
     n, c, r, _ = x.shape
     if workspace is None:
         workspace = torch.empty(shu_workspace_bytes(n, c, r), dtype=torch.uint8, device=x.device)
     arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
     lib = _lib.load()
-    _lib.check(lib.shgan_shu_fwd(_p(x), _p(conv0_w), _p(conv0_b), _p(df1_w), _p(cw), _p(gauss), _p(workspace), arr,
+    _lib.check(lib.shgan_shu_fwd(_p(x), _p(conv0_w), _p(conv0_b), _p(df1_w), _p(cw), _p(gauss), _p(packed), _p(workspace), arr,
                                 len(outs), n, c, r, lowest_res, _stream()), 'shgan_shu_fwd')
     return outs

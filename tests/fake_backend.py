@@ -259,7 +259,11 @@ def shu_workspace_bytes(n, c, r):
     return 16
 
 
-def shu_fwd(x, conv0_w, conv0_b, df1_w, cw, gauss, outs, lowest_res, workspace=None):
+def shu_pack(conv0_w, df1_w):
+    return torch.zeros(16, dtype=torch.uint8)
+
+
+def shu_fwd(x, conv0_w, conv0_b, df1_w, cw, gauss, outs, lowest_res, workspace=None, packed=None):
     """Emulated with the oracle's SHU; checks that the constants handed to the kernel are the oracle's."""
     from oracle import shgan_oracle as O
     n, c, r, _ = x.shape
@@ -278,6 +282,6 @@ def install(monkeypatch):
     import shgan_b200.engine as E
     for name in ['make_epilogue', 'conv_num_nblocks', 'conv_igemm', 'conv_up2', 'fir_nhwc', 'nchw_to_planes', 'planes_to_nchw',
                  'planes_add_nchw', 'nhwc_to_nchw_f32', 'fromrgb', 'torgb_combine', 'mbstd_append', 'dense', 'normalize_2nd_moment',
-                 'style_prep', 'style_prep_batched', 'shu_workspace_bytes', 'shu_fwd']:
+                 'style_prep', 'style_prep_batched', 'shu_workspace_bytes', 'shu_pack', 'shu_fwd']:
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(E, '_check_device', lambda dev: None)

@@ -253,6 +253,23 @@ def test_shu_golden(golden):
         assert relerr(yb[r].cpu().numpy(), ref[r]) <= 2e-5
 
 
+@pytest.mark.parametrize('n_in', [256, 512, 4, 8])
+def test_shu_large_and_small_input_res_vs_oracle(n_in):
+    """BASELINE.json config C5 sweeps the unit over input_res 4..512: sizes above 128 run their transforms as row / column
+    passes through global memory; checked against the oracle (numpy pocketfft)."""
+    from shgan_b200.model_zoo.shgan import SHU
+    sd = {k: v for k, v in O.synthetic_state_dict(256, seed=7).items() if k.startswith('encoder.shu')}
+    shu = SHU(32, 32, dfilter_freedom=[2, 3], dfilter_type='piecewise_linear', input_res=n_in, lowest_res=4)
+    shu.load_state_dict({k[len('encoder.shu.'):]: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    shu = shu.to(DEV)
+    x = rng(520 + n_in).standard_normal((2, 32, n_in, n_in)).astype(np.float32)
+    y = shu(t(x))
+    ref = O.shu_forward(sd, x, input_res=n_in)
+    assert sorted(y) == sorted(ref)
+    for r in ref:
+        assert relerr(y[r].cpu().numpy(), ref[r]) <= 2e-5, r
+
+
 def test_shu_narrow_uses_fma_mix():
     """C != 32: the fp32-FMA channel-mix kernel (the tensor-core mix needs 2C == 64) against the oracle."""
     from shgan_b200.model_zoo.shgan import SHU
