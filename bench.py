@@ -399,7 +399,7 @@ def main():
         n, h, w, c = src.shape
         return 2.0 * n * h * w * 9 * c * w_hi.shape[0] * 64            # transposed conv counted on its input grid
 
-    def fir_work(src, f, gain, pads, epi, parity_split=False):
+    def fir_work(src, f, gain, pads, epi, parity_split=False, rank1=False):
         n, ih, iw, c = src.shape
         oh, ow = ih + pads[2] + pads[3] - 3, iw + pads[0] + pads[1] - 3
         if parity_split == 2:

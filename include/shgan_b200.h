@@ -57,6 +57,19 @@ int shgan_planes_to_nchw(const void* in_hi, const void* in_lo, float* y, int N, 
  * lib/model_zoo/shgan.py:378-382 without copying the untouched channels. */
 int shgan_planes_add_nchw(void* hi, void* lo, const float* x, int N, int C, int H, int W,
                           int c_off, int c_tot, void* stream);
+/* shgan_planes_add_nchw for up to SHGAN_MAX_ADD tensors of different spatial size in one launch: band k adds
+ * x[k] [N,C,hw[k]] (NCHW fp32) into channels [c_off[k], c_off[k]+C) of the planes hi[k]/lo[k] [N,hw[k],c_tot[k]].
+ * The SHU add-back over all of its bands (lib/model_zoo/shgan.py:378-382).  work_start is filled in by the library. */
+#define SHGAN_MAX_ADD 8
+typedef struct {
+    int num;
+    void* hi[SHGAN_MAX_ADD];
+    void* lo[SHGAN_MAX_ADD];
+    const void* x[SHGAN_MAX_ADD];
+    int hw[SHGAN_MAX_ADD], c_off[SHGAN_MAX_ADD], c_tot[SHGAN_MAX_ADD];
+    long long work_start[SHGAN_MAX_ADD + 1];
+} shgan_add_batch;
+int shgan_planes_add_nchw_multi(shgan_add_batch* b, int N, int C, void* stream);
 /* NHWC fp32 -> NCHW fp32 (op-level API glue) */
 int shgan_nhwc_to_nchw_f32(const float* x, float* y, int N, int C, int H, int W, void* stream);
 
@@ -171,7 +184,11 @@ int shgan_conv_up2(const shgan_up2_desc* d, void* stream);
  * parity_split == 1: out planes are written de-interleaved as 4 tensors [N,PH,PW,C], plane
  * q=(y&1)*2+(x&1) at out_hi + q*N*PH*PW*C, element (y>>1, x>>1); PH=(OH+1)/2, PW=(OW+1)/2.
  * parity_split == 2: only the even/even samples are kept, out planes [N,PH,PW,C] (= upfirdn2d with down=2:
- * the discriminator's skip path, conv2d_resample.py:105-108). */
+ * the discriminator's skip path, conv2d_resample.py:105-108).
+ * parity_split | SHGAN_FIR_RANK1: the caller guarantees that f is an outer product fy (x) fx (the reference's
+ * [1,3,3,1] blur is).  Without the flag the library decides on the device, and a second, general-filter kernel is always
+ * launched behind the separable one (it returns at once for rank-1 filters); with it that launch is skipped. */
+#define SHGAN_FIR_RANK1 0x100
 int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void* in_lo,
                    const float* f, int fH, int fW, float gain,
                    int N, int C, int IH, int IW, int pad_x0, int pad_x1, int pad_y0, int pad_y1,

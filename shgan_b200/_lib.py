@@ -52,6 +52,18 @@ class Up2Desc(C.Structure):
     ]
 
 
+SHGAN_MAX_ADD = 8
+
+
+class AddBatch(C.Structure):
+    """shgan_add_batch (include/shgan_b200.h)."""
+    _fields_ = [
+        ('num', i32), ('hi', vp * SHGAN_MAX_ADD), ('lo', vp * SHGAN_MAX_ADD), ('x', vp * SHGAN_MAX_ADD),
+        ('hw', i32 * SHGAN_MAX_ADD), ('c_off', i32 * SHGAN_MAX_ADD), ('c_tot', i32 * SHGAN_MAX_ADD),
+        ('work_start', C.c_longlong * (SHGAN_MAX_ADD + 1)),
+    ]
+
+
 SHGAN_MAX_STYLE_LAYERS = 40
 
 
@@ -75,6 +87,7 @@ SIGNATURES = {
     'shgan_nchw_to_planes': (i32, [fp, vp, vp, fp, vp, vp] + [i32] * 6 + [vp]),
     'shgan_planes_to_nchw': (i32, [vp, vp, fp] + [i32] * 6 + [vp]),
     'shgan_planes_add_nchw': (i32, [vp, vp, fp] + [i32] * 6 + [vp]),
+    'shgan_planes_add_nchw_multi': (i32, [C.POINTER(AddBatch), i32, i32, vp]),
     'shgan_nhwc_to_nchw_f32': (i32, [fp, fp] + [i32] * 4 + [vp]),
     'shgan_conv_igemm': (i32, [C.POINTER(ConvDesc), vp]),
     'shgan_conv_num_nblocks': (i32, [i32, i32]),

@@ -522,6 +522,8 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
     SHGAN_CHECK(OH >= 1 && OW >= 1, "output must be at least 1x1");
     if (const char* m = check_epi(*epi_, C)) SHGAN_CHECK(false, m);
     SHGAN_CHECK(!epi_->rgb_w, "fused torgb is not available in the FIR epilogue");
+    const bool rank1_hint = (parity_split & SHGAN_FIR_RANK1) != 0;
+    parity_split &= ~SHGAN_FIR_RANK1;
     SHGAN_CHECK(parity_split >= 0 && parity_split <= 2, "parity_split must be 0, 1 or 2");
     SHGAN_CHECK(!parity_split || (!epi_->out_f32 && !epi_->skip_hi && !epi_->noise), "parity_split supports plane output only");
     SHGAN_CHECK((long long)N * C * ((long long)OH + 1) * (OW + 1) <= INT32_MAX, "tensor is too large");
@@ -555,6 +557,7 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
                                                                                   parity_split, ft);
         SHGAN_LAUNCH_CHECK();
         skip_rank1 = 1;
+        if (rank1_hint) return 0;     // the caller vouches for a rank-1 filter: no fallback launch for the general case
     }
     // general 4x4 filters (and channel counts that are not a multiple of 32).  Measured on B200: planes input 2.4 TB/s with
     // the TMA-staged kernel vs 2.0 TB/s with the register kernel; fp32 input + full epilogue 2.0 TB/s vs 3.1 TB/s

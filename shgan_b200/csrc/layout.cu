@@ -117,6 +117,52 @@ extern "C" int shgan_planes_add_nchw(void* hi, void* lo, const float* x, int N, 
     return shgan_nchw_to_planes(x, hi, lo, nullptr, hi, lo, N, C, H, W, c_off, c_tot, stream);
 }
 
+// feats[r][:, c_off:c_off+C] += x_r for several resolutions in ONE launch (the SHU add-back of shgan.py:378-382 over its
+// five bands): thread = (band, n, pixel, group of 8 channels); x reads are coalesced over the pixels, each thread
+// re-splits its 8 channels in place.
+namespace shgan {
+__global__ void __launch_bounds__(256)
+planes_add_multi_kernel(const shgan_add_batch b, int N, int C) {
+    const int cgs = C / 8;
+    long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; gid < b.work_start[b.num]; gid += stride) {
+        int k = 0;
+        while (gid >= b.work_start[k + 1]) ++k;
+        const long long loc = gid - b.work_start[k];
+        const int hw = b.hw[k];
+        const int p = (int)(loc % hw);
+        const long long t = loc / hw;
+        const int cg = (int)(t % cgs), n = (int)(t / cgs);
+        const float* xp = (const float*)b.x[k] + ((long long)n * C + cg * 8) * hw + p;
+        const long long idx = ((long long)n * hw + p) * b.c_tot[k] + b.c_off[k] + cg * 8;
+        float v[8];
+        load_planes8((const __half*)b.hi[k], (const __half*)b.lo[k], idx, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += __ldg(xp + (long long)j * hw);
+        store_planes8((__half*)b.hi[k], (__half*)b.lo[k], idx, v);
+    }
+}
+}  // namespace shgan
+
+extern "C" int shgan_planes_add_nchw_multi(shgan_add_batch* b, int N, int C, void* stream) {
+    SHGAN_CHECK(b && b->num >= 1 && b->num <= SHGAN_MAX_ADD, "bad batch");
+    SHGAN_CHECK(N >= 0 && C >= 8 && C % 8 == 0, "C must be a multiple of 8");
+    if (N == 0) return 0;
+    b->work_start[0] = 0;
+    for (int k = 0; k < b->num; ++k) {
+        SHGAN_CHECK(b->hi[k] && b->lo[k] && b->x[k] && b->hw[k] >= 1, "null pointer / empty band");
+        SHGAN_CHECK(b->c_off[k] >= 0 && b->c_off[k] % 8 == 0 && b->c_off[k] + C <= b->c_tot[k] && b->c_tot[k] % 8 == 0, "bad channel slice");
+        b->work_start[k + 1] = b->work_start[k] + (long long)N * (C / 8) * b->hw[k];
+    }
+    const long long total = b->work_start[b->num];
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    shgan::planes_add_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*b, N, C);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int shgan_nhwc_to_nchw_f32(const float* x, float* y, int N, int C, int H, int W, void* stream) {
     SHGAN_CHECK(x && y, "null pointer");
     if (int e = check_dims(N, C, H, W, 0, C)) return e;

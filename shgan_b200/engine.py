@@ -304,7 +304,7 @@ class GeneratorEngine:
             c1 = d['conv1']['ci']
             par = self._planes(f'e{r}.par', 4 * n, ph, ph, c1)
             ident = K.make_epilogue(out=par)
-            K.fir_nhwc(feat, self.f_applied, 1.0, (2, 2, 2, 2), ident, parity_split=True)
+            K.fir_nhwc(feat, self.f_applied, 1.0, (2, 2, 2, 2), ident, parity_split=True, rank1=self.f_sep is not None)
             srcs = [Planes(par.hi[q * n:(q + 1) * n], par.lo[q * n:(q + 1) * n]) for q in range(4)]
             a = self._planes(f'e{r}.down', n, r // 2, r // 2, d['conv1']['co'])
             self._conv(srcs, d['conv1'], P.taps_down2(3), r // 2, r // 2, epi=self._enc_epi(d['conv1'], a))
@@ -319,8 +319,9 @@ class GeneratorEngine:
                 shu_outs = self._shu_compute(feats[self.shu['input_res']], n)
             self._join()
             ch = self.shu['ch']
-            for r, o in zip(self.shu['reslist'], shu_outs):
-                K.planes_add_nchw(feats[r], o, feats[r].shape[3] - ch)   # feats[r][:, -ch:] += shu[r]  (shgan.py:378-382)
+            rl = self.shu['reslist']
+            # feats[r][:, -ch:] += shu[r] for every band (shgan.py:378-382), one launch
+            K.planes_add_nchw_multi([feats[r] for r in rl], shu_outs, [feats[r].shape[3] - ch for r in rl])
         return x_global, feats
 
     def _shu_compute(self, fin, n):
@@ -432,7 +433,7 @@ class GeneratorEngine:
                         for px in range(2):
                             self._conv([x], L0, P.taps_up2(py, px), P.up2_pass_size(h, py), P.up2_pass_size(h, px),
                                        raw=(z, 2, 2, py, px))
-                    K.fir_nhwc(z, self.f_applied, 4.0, (1, 1, 1, 1), epi)
+                    K.fir_nhwc(z, self.f_applied, 4.0, (1, 1, 1, 1), epi, rank1=self.f_sep is not None)
                 x = y
                 L, name = d['conv1'], f'b{r}.conv1'
             nz, sn = noise[name]

@@ -162,6 +162,21 @@ def planes_add_nchw(p, x, c_off):
 
 
 @_on_tensor_device
+def planes_add_nchw_multi(planes_list, xs, c_off_list):
+    """planes_list[k][..., c_off:c_off+C] += xs[k] (NCHW fp32 [N,C,h,w]) for all k in one launch."""
+    b = _lib.AddBatch()
+    b.num = len(xs)
+    n, c = xs[0].shape[0], xs[0].shape[1]
+    for k, (p, x, co) in enumerate(zip(planes_list, xs, c_off_list)):
+        _f32c(x, 'x')
+        assert x.shape[0] == n and x.shape[1] == c and tuple(p.shape[1:3]) == tuple(x.shape[2:])
+        b.hi[k] = _p(p.hi); b.lo[k] = _p(p.lo); b.x[k] = _p(x)
+        b.hw[k] = x.shape[2] * x.shape[3]; b.c_off[k] = co; b.c_tot[k] = p.shape[3]
+    lib = _lib.load()
+    _lib.check(lib.shgan_planes_add_nchw_multi(C.byref(b), n, c, _stream()), 'shgan_planes_add_nchw_multi')
+
+
+@_on_tensor_device
 def nhwc_to_nchw_f32(x):
     _f32c(x, 'x')
     n, h, w, c = x.shape
@@ -225,8 +240,12 @@ def conv_num_nblocks(co, block_n=0):
 
 
 @_on_tensor_device
-def fir_nhwc(src, f, gain, pads, epi, parity_split=False):
-    """src: Planes or fp32 NHWC tensor; pads = (pad_x0, pad_x1, pad_y0, pad_y1); f: fp32 [4,4] (as applied)."""
+FIR_RANK1 = 0x100
+
+
+def fir_nhwc(src, f, gain, pads, epi, parity_split=False, rank1=False):
+    """src: Planes or fp32 NHWC tensor; pads = (pad_x0, pad_x1, pad_y0, pad_y1); f: fp32 [4,4] (as applied).
+    rank1=True: the caller has checked (on the host, once) that f is separable -> no fallback launch (SHGAN_FIR_RANK1)."""
     lib = _lib.load()
     if isinstance(src, Planes):
         n, ih, iw, c = src.shape
@@ -236,7 +255,7 @@ def fir_nhwc(src, f, gain, pads, epi, parity_split=False):
         n, ih, iw, c = src.shape
         args = (_p(src), None, None)
     _lib.check(lib.shgan_fir_nhwc(*args, _p(f), f.shape[0], f.shape[1], float(gain), n, c, ih, iw,
-                                 pads[0], pads[1], pads[2], pads[3], C.byref(epi), int(parity_split), _stream()),
+                                 pads[0], pads[1], pads[2], pads[3], C.byref(epi), int(parity_split) | (FIR_RANK1 if rank1 else 0), _stream()),
                'shgan_fir_nhwc')
 
 

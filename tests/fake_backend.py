@@ -135,7 +135,7 @@ def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None):
     _apply_epi(acc, epi, 64)
 
 
-def fir_nhwc(src, f, gain, pads, epi, parity_split=False):
+def fir_nhwc(src, f, gain, pads, epi, parity_split=False, rank1=False):
     x = src.float() if isinstance(src, Planes) else src
     n, ih, iw, c = x.shape
     px0, px1, py0, py1 = pads
@@ -176,6 +176,11 @@ def planes_to_nchw(p, c_off=0, c=None, out=None):
 
 def planes_add_nchw(p, x, c_off):
     return nchw_to_planes(x, add=p, out=p, c_off=c_off)
+
+
+def planes_add_nchw_multi(planes_list, xs, c_off_list):
+    for p, x, co in zip(planes_list, xs, c_off_list):
+        planes_add_nchw(p, x, co)
 
 
 def nhwc_to_nchw_f32(x):
@@ -281,7 +286,7 @@ def install(monkeypatch):
     """Patch shgan_b200.kernels (and the engine's device check) with the CPU emulation."""
     import shgan_b200.engine as E
     for name in ['make_epilogue', 'conv_num_nblocks', 'conv_igemm', 'conv_up2', 'fir_nhwc', 'nchw_to_planes', 'planes_to_nchw',
-                 'planes_add_nchw', 'nhwc_to_nchw_f32', 'fromrgb', 'torgb_combine', 'mbstd_append', 'dense', 'normalize_2nd_moment',
+                 'planes_add_nchw', 'planes_add_nchw_multi', 'nhwc_to_nchw_f32', 'fromrgb', 'torgb_combine', 'mbstd_append', 'dense', 'normalize_2nd_moment',
                  'style_prep', 'style_prep_batched', 'shu_workspace_bytes', 'shu_pack', 'shu_fwd']:
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(E, '_check_device', lambda dev: None)
