@@ -239,10 +239,10 @@ def conv_num_nblocks(co, block_n=0):
     return _lib.load().shgan_conv_num_nblocks(co, block_n)
 
 
-@_on_tensor_device
 FIR_RANK1 = 0x100
 
 
+@_on_tensor_device
 def fir_nhwc(src, f, gain, pads, epi, parity_split=False, rank1=False):
     """src: Planes or fp32 NHWC tensor; pads = (pad_x0, pad_x1, pad_y0, pad_y1); f: fp32 [4,4] (as applied).
     rank1=True: the caller has checked (on the host, once) that f is separable -> no fallback launch (SHGAN_FIR_RANK1)."""
