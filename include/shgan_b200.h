@@ -135,8 +135,8 @@ typedef struct {
     int passes;                  /* 3 = fp32-class (default when 0), 1 = hi*hi only (fast, ~fp16 accuracy) */
     int impl;                    /* 0 = tcgen05 tensor-core path (the product): the halo-tile kernel for the large layers,
                                         the per-tap kernel for the small ones, chosen per layer;
-                                    1 = fp32 FMA kernel with identical operands/epilogue, kept ONLY as the on-device
-                                        cross-check of the tensor-core kernels at full layer sizes (tests);
+                                    1 = rejected by this library: the fp32 FMA cross-check kernel with identical operands /
+                                        epilogue is built into the TEST-ONLY libshgan_b200_check.so (shgan_check_conv_igemm);
                                     2 / 3 = force the per-tap / the halo-tile tensor-core kernel (tests, profiling);
                                     4 = the two-SM (cta_group::2) kernel wherever Co % 256 == 0, per-tap elsewhere */
     float acc_comp;              /* compensation of the tensor core's TRUNCATING fp32 accumulate (measured on B200: every

@@ -130,6 +130,24 @@ def load():
     return lib
 
 
+_check_lib = None
+CHECK_LIB_PATH = os.path.join(_HERE, 'lib', 'libshgan_b200_check.so')
+
+
+def load_check():
+    """TEST-ONLY library with the fp32 FMA cross-check convolution (`impl=1`); never loaded by the product path."""
+    global _check_lib
+    if _check_lib is None:
+        if not os.path.exists(CHECK_LIB_PATH):
+            raise RuntimeError(f'{CHECK_LIB_PATH} is missing: impl=1 is a test facility, build it with `python -m shgan_b200.build`')
+        lib = C.CDLL(CHECK_LIB_PATH)
+        lib.shgan_check_conv_igemm.restype = i32
+        lib.shgan_check_conv_igemm.argtypes = [C.POINTER(ConvDesc), vp]
+        lib.shgan_last_error.restype = C.c_char_p
+        _check_lib = lib
+    return _check_lib
+
+
 def check(rc, what):
     if rc != 0:
         msg = load().shgan_last_error()

@@ -16,6 +16,9 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 OBJDIR = os.path.join(LIBDIR, 'obj')
 LIB = os.path.join(LIBDIR, 'libshgan_b200.so')
+# test-only: the fp32 FMA cross-check convolution (csrc/check/*.cu).  Never loaded by the product path.
+CHECK_LIB = os.path.join(LIBDIR, 'libshgan_b200_check.so')
+CHECK_SRC = os.path.join(CSRC, 'check')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
@@ -34,7 +37,7 @@ def _headers_mtime():
 
 
 def _compile(src, verbose):
-    obj = os.path.join(OBJDIR, src[:-3] + '.o')
+    obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + '.o')
     cmd = [NVCC] + FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
     if verbose:
         print(' '.join(cmd), flush=True)
@@ -48,10 +51,11 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link the shared library.  Returns the library path."""
     os.makedirs(OBJDIR, exist_ok=True)
     hm = _headers_mtime()
-    todo, objs = [], []
-    for src in _sources():
-        obj = os.path.join(OBJDIR, src[:-3] + '.o')
-        objs.append(obj)
+    todo, objs, check_objs = [], [], []
+    check_sources = [os.path.join('check', f) for f in sorted(os.listdir(CHECK_SRC)) if f.endswith('.cu')]
+    for src in _sources() + check_sources:
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + '.o')
+        (check_objs if src in check_sources else objs).append(obj)
         sm = max(os.path.getmtime(os.path.join(CSRC, src)), hm)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < sm:
             todo.append(src)
@@ -65,6 +69,12 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    if todo or not os.path.exists(CHECK_LIB):
+        cmd = [NVCC, '-shared', '-o', CHECK_LIB] + check_objs + [os.path.join(OBJDIR, 'api.o'), '-gencode',
+                                                               'arch=compute_100a,code=sm_100a', '-cudart', 'static']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'link of the test-only check library failed:\n{r.stdout}\n{r.stderr}')
     return LIB
 
 

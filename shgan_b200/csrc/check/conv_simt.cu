@@ -6,7 +6,7 @@
 // Classic shared-memory tiled SGEMM over the implicit im2col matrix: CTA tile = 64 output pixels
 // (flattened n,y,x) x 64 output channels, K step = 16 input channels of one tap; each of the 256
 // threads owns 2 pixels x 8 channels.
-#include "conv_common.cuh"
+#include "../conv_common.cuh"
 
 namespace shgan {
 

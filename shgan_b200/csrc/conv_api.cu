@@ -40,7 +40,7 @@ extern "C" int shgan_conv_igemm(const shgan_conv_desc* d, void* stream_) {
     if (d->N == 0) return 0;
     const ConvGeom g = make_geom(*d);
     const EpiParams epi = d->mode == 0 ? make_epi(d->epi) : EpiParams{};
-    if (d->impl == 1) return launch_conv_simt(g, epi, bn, stream);
+    SHGAN_CHECK(d->impl != 1, "impl 1 (fp32 FMA cross-check) is not in the product library: it lives in the test-only libshgan_b200_check.so");
     SHGAN_CHECK(d->impl == 0 || (d->impl >= 2 && d->impl <= 4), "impl must be 0, 1, 2, 3 or 4");
     const int passes = d->passes == 0 ? 3 : d->passes;
     if (d->impl == 4 && bn == 0 && conv_pair_supported(g)) return launch_conv_pair(g, epi, passes, stream);

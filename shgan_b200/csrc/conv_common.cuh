@@ -1,5 +1,5 @@
-// Geometry shared by the two implementations of shgan_conv_igemm (conv_tc.cu: tcgen05 tensor-core
-// kernel, the product path; conv_simt.cu: plain fp32 FMA kernel kept as the on-device cross-check).
+// Geometry shared by the implementations of shgan_conv_igemm (conv_tc.cu / conv_halo.cu / conv_pair.cu: tcgen05 tensor-core
+// kernels, the product path; check/conv_simt.cu: plain fp32 FMA kernel, built into the TEST-ONLY libshgan_b200_check.so).
 #pragma once
 #include "common.cuh"
 

@@ -212,6 +212,12 @@ def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, pa
         d.epi = epi
     d.block_n = block_n; d.passes = passes; d.impl = impl
     d.acc_comp = ACC_COMP if acc_comp is None else acc_comp    # 0 = library default, < 0 = off (include/shgan_b200.h)
+    if impl == 1:       # fp32 FMA cross-check: lives in the test-only library, not in libshgan_b200.so
+        chk = _lib.load_check()
+        rc = chk.shgan_check_conv_igemm(C.byref(d), _stream())
+        if rc != 0:
+            raise RuntimeError(f'shgan_check_conv_igemm failed (code {rc}): {chk.shgan_last_error().decode()}')
+        return
     lib = _lib.load()
     _lib.check(lib.shgan_conv_igemm(C.byref(d), _stream()), 'shgan_conv_igemm')
 

@@ -70,3 +70,14 @@ def test_sass_has_tcgen05_and_tma():
         assert mnemonic in pair, mnemonic
     halo = subprocess.run([cuobjdump, '-sass', os.path.join(os.path.dirname(obj), 'conv_halo.o')], capture_output=True, text=True).stdout
     assert 'UTCHMMA' in halo and 'BRA.U.ANY' not in halo
+
+
+def test_product_library_has_no_cuda_core_convolution():
+    """The fp32 FMA cross-check kernel (impl=1) lives only in the test-only libshgan_b200_check.so."""
+    import subprocess
+    from shgan_b200 import _lib, build
+    build.build()
+    prod = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    chk = subprocess.run(['nm', '-D', '--defined-only', _lib.CHECK_LIB_PATH], capture_output=True, text=True).stdout
+    assert 'conv_simt' not in prod and 'shgan_check_conv_igemm' not in prod
+    assert 'shgan_check_conv_igemm' in chk and 'conv_simt' in chk
