@@ -89,10 +89,22 @@ class _EngineMixin:
     def _engine(self):
         owner = self.__dict__.get('_owner')
         G = owner() if owner is not None else None
-        if G is None:
+        if G is None or (getattr(G, 'encoder', None) is not self and getattr(G, 'synthesis', None) is not self):
             raise RuntimeError('this module runs through a comodgan_generator; construct Generator(mapping, encoder, '
                                'synthesis) and call it (or its .encoder/.synthesis) instead')
         return G.engine()
+
+    def __deepcopy__(self, memo):
+        # the back-reference to the owning generator must not be copied (a weakref deep-copies atomically and would keep
+        # pointing at the ORIGINAL generator's engine and parameters): a copied sub-module is unattached until a
+        # Generator adopts it (Generator.__init__ / Generator.__deepcopy__)
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != '_owner':
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
 
 @register('comodgan_encoder', version)

@@ -203,3 +203,16 @@ def test_random_mask_matches_reference_fixture(golden):
             assert np.array_equal(np.packbits(m[0].astype(np.uint8)), g[f'seed{seed}_s{size}_{k}']), (seed, size, k)
             hole = 1 - m.mean()
             assert hr[0] < hole < hr[1]
+
+
+def test_submodule_deepcopy_drops_owner(fake):
+    """copy.deepcopy(G.encoder) must not keep running through the ORIGINAL generator's engine."""
+    sd = O.synthetic_state_dict(128, seed=11, ch_base=8192, ch_max=64)
+    G = H.build_generator(128, sd, 8192, 64)
+    enc2 = copy.deepcopy(G.encoder)
+    assert '_owner' not in enc2.__dict__
+    x, _ = O.synthetic_inputs(1, 128, seed=11)
+    with pytest.raises(RuntimeError):
+        enc2(torch.from_numpy(x))
+    G2 = copy.deepcopy(G)
+    assert G2.encoder._engine() is G2.engine() and G.encoder._engine() is G.engine() and G2.engine() is not G.engine()
