@@ -45,8 +45,8 @@ struct Up2Params {
     float fx[4], fy[4];          // separable blur taps as applied (correlation order); gain folded into fy
     float acc_comp;
     int passes;
-    int chunk_slabs;             // 64-channel slabs chained in one TMEM accumulator (1, or 2 for C >= 256: fewer, longer chunks
-                                 // let the MMAs run four slabs ahead while the epilogue warps are busy with the blur)
+    int chunk_slabs;             // 64-channel slabs chained in one TMEM accumulator (1, or 4 for C >= 256: fewer, longer chunks
+                                 // let the MMAs run eight slabs ahead while the epilogue warps are busy with the blur)
     // per shift group (issue order), read by the single-thread producer / issuer loops from the constant bank:
     // instruction descriptor, TMEM column offset, A start offset and weight region offset in 16-byte descriptor units,
     // number of 64-row weight units and the first unit
@@ -473,7 +473,9 @@ extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
     for (int i = 0; i < 4; ++i) { P.fx[i] = d->fx[i]; P.fy[i] = d->fy[i] * d->gain; }
     P.acc_comp = d->acc_comp == 0.f ? SHGAN_ACC_COMP_DEFAULT : (d->acc_comp < 0.f ? 0.f : d->acc_comp);
     P.passes = d->passes == 0 ? 3 : d->passes;
-    P.chunk_slabs = (d->C / 64) % 2 == 0 && d->C >= 256 ? 2 : 1;
+    // C >= 256: four slabs (<= 192 chained MMAs per column, compensated by acc_comp) per TMEM chunk, so that the two
+    // accumulator buffers let the MMAs run a whole 512-channel tile ahead of the epilogue warps
+    P.chunk_slabs = (d->C / 64) % 4 == 0 ? 4 : ((d->C / 64) % 2 == 0 && d->C >= 256 ? 2 : 1);
     for (int sg = 0; sg < 4; ++sg) {
         P.sg_idesc[sg] = (1u << 4) | ((uint32_t)(u2_n(sg) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         P.sg_col[sg] = (uint32_t)u2_col(sg);

@@ -265,7 +265,8 @@ def _up2_reference(x, w, fy, fx, gain):
     return torch.nn.functional.conv2d(z, f[None, None].expand(co, 1, 4, 4), padding=1, groups=co)        # correlation, as applied
 
 
-UP2_SHAPES = [(2, 64, 64, 8, 8), (1, 128, 64, 20, 23), (2, 64, 128, 13, 7), (1, 256, 192, 4, 4), (3, 64, 64, 1, 2), (2, 192, 64, 33, 40)]
+UP2_SHAPES = [(2, 64, 64, 8, 8), (1, 128, 64, 20, 23), (2, 64, 128, 13, 7), (1, 256, 192, 4, 4), (3, 64, 64, 1, 2), (2, 192, 64, 33, 40),
+              (1, 512, 128, 16, 16), (1, 384, 64, 9, 9)]
 
 
 @pytest.mark.parametrize('shape', UP2_SHAPES, ids=[str(s) for s in UP2_SHAPES])
