@@ -10,7 +10,8 @@ from shgan_b200 import kernels as K, packing as P  # noqa: E402
 
 dev = 'cuda'
 LAYERS = {'b512': (16, 128, 64, 256), 'b256': (16, 256, 128, 128), 'b128': (16, 512, 256, 64), 'b64': (16, 512, 512, 32)}
-which = sys.argv[1:] or list(LAYERS)
+which = [a for a in sys.argv[1:] if a in LAYERS] or list(LAYERS)
+NO_SKIP = 'noskip' in sys.argv      # experiment: epilogue without the skip planes / the noise (how much do their loads cost?)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name in which:
     n, ci, co, h = LAYERS[name]
@@ -27,8 +28,8 @@ for name in which:
     bias = torch.randn(co, device=dev)
     nz = torch.randn(n, 1, 2 * h, 2 * h, device=dev)
     st = torch.tensor(0.1, device=dev)
-    epi = K.make_epilogue(dcoef=dc, noise=nz, noise_sn=4 * h * h, noise_strength=st, bias=bias, act=True, act_gain=2 ** 0.5, act_clamp=256.0,
-                          skip=skip, next_scale=ns, out=out)
+    epi = K.make_epilogue(dcoef=dc, noise=None if NO_SKIP else nz, noise_sn=4 * h * h, noise_strength=st, bias=bias, act=True, act_gain=2 ** 0.5,
+                          act_clamp=256.0, skip=None if NO_SKIP else skip, next_scale=ns, out=out)
     fy = fx = [0.125, 0.375, 0.375, 0.125]
     run = lambda: K.conv_up2(x, uh, ul, fx, fy, 4.0, epi)
     for _ in range(3):
