@@ -200,6 +200,12 @@ int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void* in_lo,
 int shgan_fromrgb(const float* x, const float* w /*[Co,Ci]*/, const float* bias, float wgain,
                   float act_alpha, float act_gain, float act_clamp,
                   void* out_hi, void* out_lo, int N, int Ci, int Co, int H, int W, void* stream);
+/* fromrgb with the eval loop's input preparation fused in (lib/experiments/shgan_default.py:269-274): the layer input is
+ * x = cat([mask - 0.5, real * mask]) formed in registers from real [N,Ci-1,H,W] and mask [N,1,H,W]; x is also written to
+ * x_out [N,Ci,H,W] (the composite fused into the last torgb reads it back).  w [Co,Ci] as in shgan_fromrgb. */
+int shgan_fromrgb_masked(const float* real, const float* mask, float* x_out, const float* w, const float* bias, float wgain,
+                         float act_alpha, float act_gain, float act_clamp,
+                         void* out_hi, void* out_lo, int N, int Ci, int Co, int H, int W, void* stream);
 /* img_out[n,j,y,x] = (img_prev ? upfirdn2d(img_prev, f, up=2, pad=[2,1,2,1], gain=4) : 0)
  *                    + sum_blk rgb_partial[n,y,x,blk,j] + bias[j]
  * replaces upsample2d + torgb add, lib/model_zoo/comodgan.py:331-338.  When `comp_x` != NULL also

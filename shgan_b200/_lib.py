@@ -94,6 +94,7 @@ SIGNATURES = {
     'shgan_conv_up2': (i32, [C.POINTER(Up2Desc), vp]),
     'shgan_fir_nhwc': (i32, [fp, vp, vp, fp, i32, i32, f32] + [i32] * 8 + [C.POINTER(Epilogue), i32, vp]),
     'shgan_fromrgb': (i32, [fp, fp, fp, f32, f32, f32, f32, vp, vp] + [i32] * 5 + [vp]),
+    'shgan_fromrgb_masked': (i32, [fp, fp, fp, fp, fp, f32, f32, f32, f32, vp, vp] + [i32] * 5 + [vp]),
     'shgan_torgb_combine': (i32, [fp, fp, i32, fp, fp, fp, i32, i32, i32, fp, vp, vp]),
     'shgan_prepare_input': (i32, [fp, fp, fp, i32, i32, i32, vp]),
     'shgan_composite_cat': (i32, [fp, fp, fp, i32, i32, i32, vp]),

@@ -14,10 +14,13 @@ namespace shgan {
 constexpr int FRGB_MAX_CI = 8;
 constexpr int FRGB_MAX_CO = 128;
 
+// mask != NULL: fused input preparation of the eval loop (shgan_default.py:269-274): `x` then is the real image [N,Ci-1,HW],
+// the layer input is [mask - 0.5, real * mask], and that 4-channel tensor is also written to x_out (the composite at the
+// end of the generator reads it) by the thread that owns the pixel's first channel group.
 __global__ void __launch_bounds__(256)
-fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float wgain,
-               float act_alpha, float act_gain, float act_clamp, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-               int N, int Ci, int Co, int HW) {
+fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ x_out, const float* __restrict__ w,
+               const float* __restrict__ bias, float wgain, float act_alpha, float act_gain, float act_clamp,
+               __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int Ci, int Co, int HW) {
     __shared__ __align__(16) float s_w[FRGB_MAX_CI * FRGB_MAX_CO];   // transposed [i][o]: a thread's 8 outputs are 2 x LDS.128,
     __shared__ __align__(16) float s_b[FRGB_MAX_CO];                 // conflict-free across the warp's 8 channel groups
     for (int i = threadIdx.x; i < Co * Ci; i += blockDim.x) s_w[(i % Ci) * Co + i / Ci] = w[i] * wgain;
@@ -32,8 +35,20 @@ fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
         const int n = (int)(pix / HW);
         const int p = (int)(pix - (long long)n * HW);
         float xin[FRGB_MAX_CI];
+        if (mask) {
+            const float m = __ldg(mask + (long long)n * HW + p);
+            xin[0] = m - 0.5f;
 #pragma unroll
-        for (int i = 0; i < FRGB_MAX_CI; ++i) xin[i] = i < Ci ? __ldg(x + ((long long)n * Ci + i) * HW + p) : 0.f;
+            for (int i = 1; i < FRGB_MAX_CI; ++i) xin[i] = i < Ci ? __ldg(x + ((long long)n * (Ci - 1) + (i - 1)) * HW + p) * m : 0.f;
+            if (cg == 0) {
+#pragma unroll
+                for (int i = 0; i < FRGB_MAX_CI; ++i)
+                    if (i < Ci) x_out[((long long)n * Ci + i) * HW + p] = xin[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < FRGB_MAX_CI; ++i) xin[i] = i < Ci ? __ldg(x + ((long long)n * Ci + i) * HW + p) : 0.f;
+        }
         float v[8];
         {
             const float4 b0 = *reinterpret_cast<const float4*>(s_b + cg * 8), b1 = *reinterpret_cast<const float4*>(s_b + cg * 8 + 4);
@@ -266,7 +281,24 @@ extern "C" int shgan_fromrgb(const float* x, const float* w, const float* bias, 
     const long long total = (long long)N * H * W * (Co / 8);
     long long blocks = ceil_div64(total, 256);
     if (blocks > 148LL * 32) blocks = 148LL * 32;
-    fromrgb_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, w, bias, wgain, act_alpha, act_gain, act_clamp,
+    fromrgb_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, w, bias, wgain, act_alpha, act_gain, act_clamp,
+                                                                       (__half*)out_hi, (__half*)out_lo, N, Ci, Co, H * W);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int shgan_fromrgb_masked(const float* real, const float* mask, float* x_out, const float* w, const float* bias,
+                                    float wgain, float act_alpha, float act_gain, float act_clamp, void* out_hi, void* out_lo,
+                                    int N, int Ci, int Co, int H, int W, void* stream) {
+    SHGAN_CHECK(real && mask && x_out && w && out_hi && out_lo, "null pointer");
+    SHGAN_CHECK(Ci >= 2 && Ci <= FRGB_MAX_CI, "Ci (mask channel + image channels) must be in 2..8");
+    SHGAN_CHECK(Co >= 8 && Co % 8 == 0 && Co <= FRGB_MAX_CO, "Co must be a multiple of 8, at most 128");
+    SHGAN_CHECK(N >= 0 && H >= 1 && W >= 1 && (long long)N * Co * H * W <= INT32_MAX, "bad tensor size");
+    if (N == 0) return 0;
+    const long long total = (long long)N * H * W * (Co / 8);
+    long long blocks = ceil_div64(total, 256);
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    fromrgb_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(real, mask, x_out, w, bias, wgain, act_alpha, act_gain, act_clamp,
                                                                        (__half*)out_hi, (__half*)out_lo, N, Ci, Co, H * W);
     SHGAN_LAUNCH_CHECK();
     return 0;

@@ -281,8 +281,15 @@ class GeneratorEngine:
     def encoder(self, x):
         """shgan.Encoder.forward (shgan.py:361-383) -> (x_global fp32 [N,oc_n], feats {res: Planes})."""
         self._ensure()
-        x = x.contiguous().float()
-        n, _, R, _ = x.shape
+        masked = isinstance(x, (tuple, list))      # (real [N,3,R,R], mask [N,1,R,R]): input preparation fused into fromrgb
+        if masked:
+            real, mask = x[0].contiguous().float(), x[1].contiguous().float()
+            n, _, R, _ = real.shape
+            x = self._f32('x.prepared', n, real.shape[1] + 1, R, R)     # written by the fromrgb kernel, read by the composite
+            self._prepared_x = x
+        else:
+            x = x.contiguous().float()
+            n, _, R, _ = x.shape
         feats = {}
         a = None
         ident = None
@@ -292,7 +299,11 @@ class GeneratorEngine:
             c = d['conv0']['ci']
             if 'fromrgb' in d:
                 w, b, wg = d['fromrgb']
-                a = K.fromrgb(x, w, b, wg, self.eact.alpha, self.eact.gain, self.eact.clamp, self._planes(f'e{r}.rgb', n, r, r, c))
+                if masked:      # x = cat([mask - 0.5, real * mask]) (shgan_default.py:269-274) formed inside the kernel
+                    a = K.fromrgb_masked(real, mask, x, w, b, wg, self.eact.alpha, self.eact.gain, self.eact.clamp,
+                                         self._planes(f'e{r}.rgb', n, r, r, c))
+                else:
+                    a = K.fromrgb(x, w, b, wg, self.eact.alpha, self.eact.gain, self.eact.clamp, self._planes(f'e{r}.rgb', n, r, r, c))
             feat = self._planes(f'e{r}.feat', n, r, r, d['conv0']['co'])
             self._conv([a], d['conv0'], P.taps_plain(3, 3), r, r, epi=self._enc_epi(d['conv0'], feat))
             feats[r] = feat
@@ -464,19 +475,22 @@ class GeneratorEngine:
         captured once per (shape, noise_mode, composite, passes, impl) and replayed; torch's graph-safe Philox keeps
         noise_mode='random' drawing fresh noise on every replay.  The returned tensors are engine-owned buffers."""
         self._ensure()
-        if not (self.graphs and x.is_cuda):
+        masked = isinstance(x, (tuple, list))      # (real, mask): see encoder()
+        xin = list(x) if masked else [x]
+        if not (self.graphs and xin[0].is_cuda):
             return self._forward_eager(x, z, noise_mode, composite)
-        key = (tuple(x.shape), tuple(z.shape), noise_mode, composite, self.passes, self.impl)
+        key = (tuple(tuple(t.shape) for t in xin), tuple(z.shape), noise_mode, composite, self.passes, self.impl, self.fuse_up2)
         entry = self._graphs.get(key)
         if entry is None:
-            xs = x.detach().contiguous().float().clone()
+            xs = [t.detach().contiguous().float().clone() for t in xin]
             zs = z.detach().contiguous().float().clone()
             cur = torch.cuda.current_stream(self.dev)
             side = torch.cuda.Stream(device=self.dev)
             side.wait_stream(cur)
             rng = torch.cuda.get_rng_state(self.dev)
+            xarg = tuple(xs) if masked else xs[0]
             with torch.cuda.stream(side):      # warm-up: allocates the persistent buffers, loads the kernels
-                self._forward_eager(xs, zs, noise_mode, composite)
+                self._forward_eager(xarg, zs, noise_mode, composite)
             cur.wait_stream(side)
             torch.cuda.synchronize(self.dev)
             torch.cuda.set_rng_state(rng, self.dev)   # the warm-up must not consume the caller's random stream
@@ -487,14 +501,15 @@ class GeneratorEngine:
             gc.disable()
             try:
                 with torch.cuda.graph(graph):
-                    out = self._forward_eager(xs, zs, noise_mode, composite)
+                    out = self._forward_eager(xarg, zs, noise_mode, composite)
             finally:
                 if gc_was_enabled:
                     gc.enable()
             entry = (graph, xs, zs, out)
             self._graphs[key] = entry
         graph, xs, zs, out = entry
-        xs.copy_(x, non_blocking=True)
+        for dst, src in zip(xs, xin):
+            dst.copy_(src, non_blocking=True)
         zs.copy_(z, non_blocking=True)
         graph.replay()
         return out
@@ -511,8 +526,11 @@ class GeneratorEngine:
                     t.record_stream(torch.cuda.current_stream())
         num_ws = self.G.num_ws
         ws = w.unsqueeze(1).expand(w.shape[0], num_ws, w.shape[1])
-        x = x.contiguous().float()
+        if not isinstance(x, (tuple, list)):
+            x = x.contiguous().float()
         x_global, feats = self.encoder(x)
+        if isinstance(x, (tuple, list)):
+            x = self._prepared_x          # the 4-channel network input the fromrgb kernel wrote
         self._join()
         return self.synthesis(x_global, feats, ws, noise_mode=noise_mode, comp_x=x if composite else None, noise=noise)
 

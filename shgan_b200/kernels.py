@@ -277,6 +277,17 @@ def fromrgb(x, w, bias, wgain, act_alpha, act_gain, act_clamp, out):
 
 
 @_on_tensor_device
+def fromrgb_masked(real, mask, x_out, w, bias, wgain, act_alpha, act_gain, act_clamp, out):
+    """fromrgb over x = cat([mask - 0.5, real * mask]) formed on the fly (shgan_default.py:269-274); also writes x_out."""
+    _f32c(real, 'real'); _f32c(mask, 'mask'); _f32c(x_out, 'x_out')
+    n, c3, h, wd = real.shape
+    lib = _lib.load()
+    _lib.check(lib.shgan_fromrgb_masked(_p(real), _p(mask), _p(x_out), _p(w), _p(bias), wgain, act_alpha, act_gain, act_clamp,
+                                       _p(out.hi), _p(out.lo), n, c3 + 1, out.shape[3], h, wd, _stream()), 'shgan_fromrgb_masked')
+    return out
+
+
+@_on_tensor_device
 def torgb_combine(img_prev, rgb_partial, bias, f, img_out, comp_x=None, comp_out=None):
     n, _, h, w = img_out.shape
     lib = _lib.load()

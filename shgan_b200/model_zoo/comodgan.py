@@ -266,6 +266,13 @@ class Generator(Generator_StyleGan):
         img = self.engine().forward(x, z, noise_mode=noise_mode)
         return img[:, :self.img_channels].clone()
 
+    def forward_inpaint(self, real, mask, z, noise_mode='random'):
+        """The eval loop's whole per-batch device work in one fused pass (lib/experiments/shgan_default.py:257-274):
+        x = cat([mask - 0.5, real * mask]) is formed inside the fromrgb kernel, the composite + uint8 quantisation inside
+        the last torgb kernel.  real [N,3,R,R] in [-1,1], mask [N,1,R,R] in {0,1} -> (img fp32, composite uint8)."""
+        img, comp = self.engine().forward((real, mask), z, noise_mode=noise_mode, composite=True)
+        return img.clone(), comp
+
     def forward_composite(self, x, z, noise_mode='random'):
         """Generator forward fused with the eval loop's composite + uint8 quantisation
         (lib/experiments/shgan_default.py:257-262) -> (img fp32, composite uint8)."""

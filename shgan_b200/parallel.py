@@ -101,9 +101,12 @@ class EvalLoop:
             items = [dataset(i) for i in idx]
             real = torch.stack([it[0] for it in items]).to(self.device, non_blocking=True)
             mask = torch.stack([it[1] for it in items])[:, None].to(self.device, non_blocking=True)
-            x = self.prepare(real, mask)
             z = torch.stack([self.latent(i) for i in idx]).to(self.device, non_blocking=True)
-            _, fake_u8 = self.G.forward_composite(x, z, noise_mode=noise_mode)
+            if real.is_cuda and hasattr(self.G, 'forward_inpaint'):
+                # mask / erase / concat (shgan_default.py:269-274) fused into the first kernel of the generator
+                _, fake_u8 = self.G.forward_inpaint(real.contiguous().float(), mask.contiguous().float(), z, noise_mode=noise_mode)
+            else:
+                _, fake_u8 = self.G.forward_composite(self.prepare(real, mask), z, noise_mode=noise_mode)
             f_fake = self.detector(fake_u8).to(torch.float64)
             f_real = self.detector((real * 127.5 + 127.5).clamp(0, 255).to(torch.uint8)).to(torch.float64)
             col = torch.tensor(idx, dtype=torch.float64, device=f_fake.device)[:, None]

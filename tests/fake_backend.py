@@ -198,6 +198,11 @@ def fromrgb(x, w, bias, wgain, act_alpha, act_gain, act_clamp, out):
     return out
 
 
+def fromrgb_masked(real, mask, x_out, w, bias, wgain, act_alpha, act_gain, act_clamp, out):
+    x_out.copy_(torch.cat([mask - 0.5, real * mask], dim=1))
+    return fromrgb(x_out, w, bias, wgain, act_alpha, act_gain, act_clamp, out)
+
+
 def torgb_combine(img_prev, rgb_partial, bias, f, img_out, comp_x=None, comp_out=None):
     n, _, h, w = img_out.shape
     v = rgb_partial[..., :3].sum(3).permute(0, 3, 1, 2) + bias.view(1, 3, 1, 1)
@@ -286,7 +291,7 @@ def install(monkeypatch):
     """Patch shgan_b200.kernels (and the engine's device check) with the CPU emulation."""
     import shgan_b200.engine as E
     for name in ['make_epilogue', 'conv_num_nblocks', 'conv_igemm', 'conv_up2', 'fir_nhwc', 'nchw_to_planes', 'planes_to_nchw',
-                 'planes_add_nchw', 'planes_add_nchw_multi', 'nhwc_to_nchw_f32', 'fromrgb', 'torgb_combine', 'mbstd_append', 'dense', 'normalize_2nd_moment',
+                 'planes_add_nchw', 'planes_add_nchw_multi', 'nhwc_to_nchw_f32', 'fromrgb', 'fromrgb_masked', 'torgb_combine', 'mbstd_append', 'dense', 'normalize_2nd_moment',
                  'style_prep', 'style_prep_batched', 'shu_workspace_bytes', 'shu_pack', 'shu_fwd']:
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(E, '_check_device', lambda dev: None)

@@ -321,3 +321,18 @@ def test_generator_tc_fused_up2_equals_unfused():
     b = G(t(x), t(z), None, noise_mode='const').cpu().numpy()
     eng.fuse_up2 = True
     assert np.abs(a - b).max() <= 2e-4 * max(1.0, np.abs(b).max()), np.abs(a - b).max()
+
+
+def test_generator_tc_forward_inpaint_equals_prepared_input():
+    """Input preparation fused into fromrgb (shgan_default.py:269-274): forward_inpaint(real, mask, z) must reproduce
+    forward_composite(cat([mask - 0.5, real * mask]), z) bit for bit, eagerly and under graph replay."""
+    sd = O.synthetic_state_dict(128, seed=11, ch_base=8192, ch_max=64)
+    G = H.build_generator(128, sd, 8192, 64, device=DEV)
+    x, z = O.synthetic_inputs(3, 128, seed=11)
+    mask = t(x[:, 0:1] + 0.5)
+    real = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(3)).to(DEV) * 2 - 1
+    xin = torch.cat([mask - 0.5, real * mask], dim=1)
+    for _ in range(2):
+        img_a, comp_a = G.forward_composite(xin, t(z), noise_mode='const')
+        img_b, comp_b = G.forward_inpaint(real, mask, t(z), noise_mode='const')
+        assert torch.equal(img_a, img_b) and torch.equal(comp_a, comp_b)

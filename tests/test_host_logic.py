@@ -216,3 +216,17 @@ def test_submodule_deepcopy_drops_owner(fake):
         enc2(torch.from_numpy(x))
     G2 = copy.deepcopy(G)
     assert G2.encoder._engine() is G2.engine() and G.encoder._engine() is G.engine() and G2.engine() is not G.engine()
+
+
+def test_forward_inpaint_host_logic(fake):
+    """forward_inpaint((real, mask)) == forward_composite(cat([mask - 0.5, real * mask])) through the emulated kernels."""
+    sd = O.synthetic_state_dict(128, seed=11, ch_base=8192, ch_max=64)
+    G = H.build_generator(128, sd, 8192, 64)
+    G.engine(graphs=False)
+    x, z = O.synthetic_inputs(1, 128, seed=11)
+    mask = torch.from_numpy(x[:, 0:1] + 0.5)
+    real = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    xin = torch.cat([mask - 0.5, real * mask], dim=1)
+    img_a, comp_a = G.forward_composite(xin, torch.from_numpy(z), noise_mode='const')
+    img_b, comp_b = G.forward_inpaint(real, mask, torch.from_numpy(z), noise_mode='const')
+    assert torch.equal(img_a, img_b) and torch.equal(comp_a, comp_b)
