@@ -3,24 +3,24 @@
 // -> complex -> per band: crop, Gaussian mask, un-shift, torch.fft.irfftn).
 //
 // Three launches for input_res <= 128 (the released model: 64), spectra in shared memory / registers inside each:
-//   1. shu_rfft2_kernel   one CTA per (n,c) plane: radix-2 shared-memory FFT, two real rows packed into one
-//                         complex transform, columns transformed in place, 1/(R*R) scaling ('forward' norm) and
-//                         the DC-to-centre row shift folded into the store.  -> spec1 [N, 2C, R, R/2+1] (re | im)
-//   2. channel mixing, ONE kernel.  C == 32 (the released model): shu_mix_mma_kernel -- per tile of 64 frequency bins the
-//                         64 spectrum channels are split into fp16 hi/lo in shared memory and both 1x1 convolutions run
-//                         on the tensor cores (warp-level mma.sync m16n8k16, hi*hi + lo*hi + hi*lo, fp32 accumulators in
-//                         registers): conv0 + bias + ReLU, whose result never leaves shared memory, then the six anchor
-//                         filters df1[:, o*6+k] blended per bin by cw[k,bin] in registers (heterogeneous filter).  The
-//                         packed fp16 weights are prepared ONCE by shgan_shu_pack (engine.refresh), not per forward.
+//   1. forward rfft2.  input_res 64 (the released model): shu_fft64.cu -- register-resident radix-8 transforms, bulk-copied
+//                         planes, spectrum written kx-major.  Other sizes: shu_rfft2_kernel, one CTA per (n,c) plane, radix-2
+//                         shared-memory FFT, two real rows packed into one complex transform, 1/(R*R) scaling ('forward' norm)
+//                         and the DC-to-centre row shift folded into the store.  -> spec1 [N, 2C, bins] (re | im)
+//   2. channel mixing, ONE kernel.  C == 32 (the released model): shu_mix_tc.cu -- both 1x1 convolutions on the tcgen05
+//                         tensor cores (conv0 + bias + ReLU, whose result never leaves shared memory, then the anchor filters
+//                         of the heterogeneous filter blended per bin by cw in registers); the packed fp16 hi/lo weights are
+//                         prepared ONCE by shgan_shu_pack (engine.refresh), not per forward.
 //                         Any other C: shu_mix_kernel, per-bin fp32 FMA mixing with the weights in shared memory.
-//                         -> spec2 [N, 2C, R, R/2+1]
-//   3. shu_irfft2_kernel  one CTA per (n,c,band): crop + Gaussian band mask + un-shift folded into the load,
+//                         -> spec2 [N, 2C, bins]
+//   3. per-band inverse.  input_res 64: shu_fft64.cu, all bands of a plane in one CTA.  Other sizes: shu_irfft2_kernel, one CTA
+//                         per (n,c,band): crop + Gaussian band mask + un-shift folded into the load,
 //                         inverse column FFTs, Hermitian extension with the DC/Nyquist imaginary parts dropped
 //                         (C2R semantics of pocketfft/cuFFT on non-Hermitian input), two rows per complex FFT.
 // input_res 256 / 512 (BASELINE.json config C5 sweeps the unit up to 512): a plane no longer fits one SM's shared memory;
 // the transforms then run as a row pass and a column pass through a float2 scratch in global memory
 // (shu_fft_rows_kernel / shu_fft_cols_kernel and their inverses), same arithmetic, five launches more.
-#include "conv_common.cuh"
+#include "shu_internal.cuh"
 
 namespace shgan {
 
@@ -176,11 +176,6 @@ shu_mix_kernel(const float* __restrict__ spec1, const float* __restrict__ conv0_
 }
 
 // ---- 3. per-band inverse rfft2 -----------------------------------------------------------------
-struct ShuBands {
-    float* out[8];
-    int gauss_off[8];   // float offset of band k's mask inside `gauss`
-    int num_bands, lowest_log2;
-};
 
 // grid (N*C, num_bands); dynamic smem sized for the largest band: colbuf [r][rh] + rowbuf [r/2][r] + tw [R/2]
 __global__ void __launch_bounds__(256)
@@ -346,158 +341,6 @@ shu_ifft_rows_kernel(const float2* __restrict__ tmp, float* __restrict__ out, in
     }
 }
 
-// ---- 2b. tensor-core channel mix for C == 32 (64 spectrum channels) ---------------------------------
-// Packed weights (shgan_shu_pack, once per parameter set): 7 matrices [64 out][64 in] as fp16 hi and lo planes, rows padded to
-// 72 halves (144 B: conflict-free ldmatrix): matrix 0 = conv0.weight[o][i]; matrix 1+k = W1_k[o2][o] = df1[o][o2*6+k].
-constexpr int MM_LD = 72;                          // smem / packed row pitch in halves
-constexpr int MM_MAT = 64 * MM_LD;                 // halves per matrix plane
-constexpr int MM_TB = 64;                          // frequency bins per tile
-constexpr int MM_W_HALVES = 7 * 2 * MM_MAT;        // all packed weights
-constexpr int MM_SMEM_BYTES = (MM_W_HALVES + 4 * MM_MAT) * 2 + (64 + 6 * MM_TB) * 4;   // weights | X hi/lo | T hi/lo | bias | cw tile
-
-__global__ void __launch_bounds__(256)
-shu_pack_kernel(const float* __restrict__ conv0_w, const float* __restrict__ df1_w, __half* __restrict__ packed) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (int i = gid; i < 7 * 64 * MM_LD; i += stride) {
-        const int m = i / MM_MAT, r = (i / MM_LD) % 64, c = i % MM_LD;
-        float v = 0.f;
-        if (c < 64) v = m == 0 ? __ldg(conv0_w + r * 64 + c) : __ldg(df1_w + c * 384 + r * 6 + (m - 1));
-        __half h, l;
-        split_f32(v, h, l);
-        packed[(m * 2) * MM_MAT + r * MM_LD + c] = h;
-        packed[(m * 2 + 1) * MM_MAT + r * MM_LD + c] = l;
-    }
-}
-
-__device__ __forceinline__ void ldsm_x4(uint32_t* r, const __half* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __half* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// acc[nt][4] (+)= W[mt*16 .. +16][0..64) * B[0..64)[nh*32 + nt*8 .. +8), three split-precision passes.
-// W hi/lo: [64][MM_LD] row-major (A operand); B hi/lo: [64 k][MM_LD] with the bins contiguous (B operand via ldmatrix.trans)
-__device__ __forceinline__ void mix_gemm(float acc[4][4], const __half* w_hi, const __half* w_lo, const __half* b_hi,
-                                         const __half* b_lo, int mt, int nh, int lane) {
-    const int lrow = lane & 15, lcol = (lane >> 4) * 8;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-        uint32_t ah[4], al[4];
-        ldsm_x4(ah, w_hi + (mt * 16 + lrow) * MM_LD + ks * 16 + lcol);
-        ldsm_x4(al, w_lo + (mt * 16 + lrow) * MM_LD + ks * 16 + lcol);
-#pragma unroll
-        for (int np = 0; np < 2; ++np) {
-            uint32_t bh[4], bl[4];
-            ldsm_x4_trans(bh, b_hi + (ks * 16 + lrow) * MM_LD + nh * 32 + np * 16 + lcol);
-            ldsm_x4_trans(bl, b_lo + (ks * 16 + lrow) * MM_LD + nh * 32 + np * 16 + lcol);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                float* d = acc[np * 2 + j];
-                mma_16816(d, ah, bh[2 * j], bh[2 * j + 1]);
-                mma_16816(d, al, bh[2 * j], bh[2 * j + 1]);
-                mma_16816(d, ah, bl[2 * j], bl[2 * j + 1]);
-            }
-        }
-    }
-}
-
-// persistent grid over tiles (n, 64 bins); 256 threads = 8 warps: warp w owns output channels (w & 3) * 16 .. +16 and bins
-// (w >> 2) * 32 .. +32 of the tile
-__global__ void __launch_bounds__(256, 1)
-shu_mix_mma_kernel(const float* __restrict__ spec1, const __half* __restrict__ packed, const float* __restrict__ conv0_b,
-                   const float* __restrict__ cw, float* __restrict__ spec2, int N, int bins, float scale) {
-    extern __shared__ __align__(16) uint8_t smm[];
-    __half* w_s = reinterpret_cast<__half*>(smm);                 // [7][2][64][MM_LD]
-    __half* x_hi = w_s + MM_W_HALVES;
-    __half* x_lo = x_hi + MM_MAT;
-    __half* t_hi = x_lo + MM_MAT;
-    __half* t_lo = t_hi + MM_MAT;
-    float* b_s = reinterpret_cast<float*>(t_lo + MM_MAT);         // [64]
-    float* cw_s = b_s + 64;                                       // [6][MM_TB]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = warp & 3, nh = warp >> 2, g = lane >> 2, t4 = lane & 3;
-    for (int i = threadIdx.x; i < MM_W_HALVES / 8; i += blockDim.x)
-        reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(packed) + i);
-    if (threadIdx.x < 64) b_s[threadIdx.x] = __ldg(conv0_b + threadIdx.x);
-    const int tiles_per_n = (bins + MM_TB - 1) / MM_TB;
-    const float inv_scale = 1.f / scale;
-    for (int tile = blockIdx.x; tile < N * tiles_per_n; tile += gridDim.x) {
-        const int n = tile / tiles_per_n, bin0 = (tile - n * tiles_per_n) * MM_TB;
-        __syncthreads();                                          // previous tile's readers of X / cw are done (and the weights are in)
-        // X tile: 64 channels x 64 bins, x scale (the 'forward'-normalised spectrum is tiny: keep it in fp16's normal range)
-        for (int i = threadIdx.x; i < 64 * MM_TB; i += blockDim.x) {
-            const int ch = i >> 6, b = i & 63;
-            const float v = bin0 + b < bins ? __ldg(spec1 + ((long long)n * 64 + ch) * bins + bin0 + b) * scale : 0.f;
-            __half h, l;
-            split_f32(v, h, l);
-            x_hi[ch * MM_LD + b] = h;
-            x_lo[ch * MM_LD + b] = l;
-        }
-        for (int i = threadIdx.x; i < 6 * MM_TB; i += blockDim.x) {
-            const int k = i >> 6, b = i & 63;
-            cw_s[i] = bin0 + b < bins ? __ldg(cw + (long long)k * bins + bin0 + b) : 0.f;
-        }
-        __syncthreads();
-        // conv0 (1x1) + bias + ReLU (shgan.py:319-321) -> T, kept in shared memory as the next GEMM's B operand (x scale again)
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-        mix_gemm(acc, w_s, w_s + MM_MAT, x_hi, x_lo, mt, nh, lane);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int o = mt * 16 + g + hh * 8, b = nh * 32 + nt * 8 + 2 * t4;
-                const float bo = b_s[o];
-                const float v0 = fmaxf(fmaf(acc[nt][2 * hh], inv_scale, bo), 0.f) * scale;
-                const float v1 = fmaxf(fmaf(acc[nt][2 * hh + 1], inv_scale, bo), 0.f) * scale;
-                const __half2 h2 = __floats2half2_rn(v0, v1);
-                const float2 f2 = __half22float2(h2);
-                *reinterpret_cast<__half2*>(t_hi + o * MM_LD + b) = h2;
-                *reinterpret_cast<__half2*>(t_lo + o * MM_LD + b) = __floats2half2_rn(v0 - f2.x, v1 - f2.y);
-            }
-        }
-        __syncthreads();
-        // heterogeneous filter (shgan.py:143-160): out = sum_k cw[k,bin] * (W1_k . T)
-        float out[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) out[i][0] = out[i][1] = out[i][2] = out[i][3] = 0.f;
-#pragma unroll 1
-        for (int k = 0; k < 6; ++k) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-            const __half* wk = w_s + (1 + k) * 2 * MM_MAT;
-            mix_gemm(acc, wk, wk + MM_MAT, t_hi, t_lo, mt, nh, lane);
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const float2 c2 = *reinterpret_cast<const float2*>(cw_s + k * MM_TB + nh * 32 + nt * 8 + 2 * t4);
-                out[nt][0] = fmaf(acc[nt][0], c2.x, out[nt][0]); out[nt][1] = fmaf(acc[nt][1], c2.y, out[nt][1]);
-                out[nt][2] = fmaf(acc[nt][2], c2.x, out[nt][2]); out[nt][3] = fmaf(acc[nt][3], c2.y, out[nt][3]);
-            }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int o = mt * 16 + g + hh * 8, b = bin0 + nh * 32 + nt * 8 + 2 * t4;
-                float* dst = spec2 + ((long long)n * 64 + o) * bins + b;
-                if (b + 1 < bins && (bins & 1) == 0) *reinterpret_cast<float2*>(dst) = make_float2(out[nt][2 * hh] * inv_scale, out[nt][2 * hh + 1] * inv_scale);
-                else {
-                    if (b < bins) dst[0] = out[nt][2 * hh] * inv_scale;
-                    if (b + 1 < bins) dst[1] = out[nt][2 * hh + 1] * inv_scale;
-                }
-            }
-        }
-    }
-}
-
 static inline int log2_exact(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -508,14 +351,15 @@ static inline int log2_exact(int v) {
 
 using namespace shgan;
 
-extern "C" int64_t shgan_shu_packed_bytes(int C) { return C == 32 ? (int64_t)MM_W_HALVES * 2 : 16; }
+extern "C" int64_t shgan_shu_packed_bytes(int C) { return C == 32 ? (int64_t)SHU_PACKED_BYTES : 16; }
+
+namespace shgan { int launch_shu_pack_tc(const float* conv0_w, const float* df1_w, void* packed, cudaStream_t stream); }
 
 extern "C" int shgan_shu_pack(const float* conv0_w, const float* df1_w, void* packed, int C, void* stream) {
     SHGAN_CHECK(conv0_w && df1_w && packed, "null pointer");
     if (C != 32) return 0;                 // only the tensor-core mix has packed operands
-    shu_pack_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(conv0_w, df1_w, (__half*)packed);
-    SHGAN_LAUNCH_CHECK();
-    return 0;
+    SHGAN_CHECK(((uintptr_t)packed & 15) == 0, "packed buffer must be 16-byte aligned");
+    return launch_shu_pack_tc(conv0_w, df1_w, packed, (cudaStream_t)stream);
 }
 
 extern "C" int64_t shgan_shu_workspace_bytes(int N, int C, int R) {
@@ -537,6 +381,7 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     SHGAN_CHECK(num_bands == log2R - log2low + 1 && num_bands <= 8, "num_bands must be log2(input_res/lowest_res)+1");
     SHGAN_CHECK(C >= 4 && C <= 32 && C % 4 == 0, "C must be a multiple of 4 in 4..32");
     SHGAN_CHECK(N >= 0 && (long long)N * C <= INT32_MAX / (R * R), "bad batch size");
+    SHGAN_CHECK(((uintptr_t)spec_ws & 15) == 0, "workspace must be 16-byte aligned");
     if (N == 0) return 0;
     const int Rh = R / 2 + 1, K2 = 2 * C, bins = R * Rh;
     float* spec1 = (float*)spec_ws;
@@ -545,18 +390,36 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     float2* tmp = (float2*)extra;                                  // only when R > 128
     if (R > 128) extra += (long long)N * C * bins * sizeof(float2);
 
+    ShuBands bands;
+    bands.num_bands = num_bands;
+    bands.lowest_log2 = log2low;
+    int off = 0;
+    bool aligned = ((uintptr_t)x & 15) == 0;
+    for (int k = 0; k < num_bands; ++k) {
+        const int r = lowest_res << k;
+        SHGAN_CHECK(outs[k], "null output pointer");
+        bands.out[k] = outs[k];
+        bands.gauss_off[k] = off;
+        off += r * (r / 2 + 1);
+        aligned = aligned && ((uintptr_t)outs[k] & 15) == 0;
+    }
+    // the released model's size: register-resident radix-8 transforms (shu_fft64.cu), spectra kx-major between the kernels;
+    // needs 16-byte aligned planes for its bulk copies
+    const bool fast64 = R == 64 && C == 32 && lowest_res >= 4 && aligned;
+
     static DeviceInit once;
     int num_sms = 148;
     if (int e = device_init(once, &num_sms, []() -> int {
             SHGAN_CUDA(cudaFuncSetAttribute(shu_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             SHGAN_CUDA(cudaFuncSetAttribute(shu_irfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             SHGAN_CUDA(cudaFuncSetAttribute(shu_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            SHGAN_CUDA(cudaFuncSetAttribute(shu_mix_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
             return 0;
         })) return e;
     const int Rs = R < 128 ? R : 128;       // size the single-CTA transforms see
     const size_t fft_smem_bytes = ((size_t)(Rs / 2) * Rs + (size_t)Rs * (Rs / 2 + 1) + Rs / 2) * sizeof(float2);
-    if (R <= 128) {
+    if (fast64) {
+        if (int e = launch_shu_rfft2_r64(x, spec1, N, C, stream)) return e;
+    } else if (R <= 128) {
         shu_rfft2_kernel<<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, C, R, log2R);
         SHGAN_LAUNCH_CHECK();
     } else {
@@ -568,16 +431,13 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     }
 
     if (C == 32) {
-        const __half* packed = (const __half*)packed_w;
+        const void* packed = packed_w;
         if (!packed) {                       // op-level callers without a prepared weight set: pack into the workspace
             if (int e = shgan_shu_pack(conv0_w, df1_w, extra, C, stream)) return e;
-            packed = (const __half*)extra;
+            packed = extra;
         }
-        const long long tiles = (long long)N * ceil_div(bins, MM_TB);
-        const int grid = (int)(tiles < num_sms ? tiles : num_sms);
         // |X_forward-normalised| <= max|x| <= 256 (lrelu_agc clamp): x R stays far below fp16 max for R <= 128; larger R use 128
-        shu_mix_mma_kernel<<<grid, 256, MM_SMEM_BYTES, stream>>>(spec1, packed, conv0_b, cw, spec2, N, bins, (float)(R < 128 ? R : 128));
-        SHGAN_LAUNCH_CHECK();
+        if (int e = launch_shu_mix_tc(spec1, packed, conv0_b, cw, spec2, N, R, fast64 ? 1 : 0, (float)(R < 128 ? R : 128), stream)) return e;
     } else {
         const size_t mix_smem = ((size_t)K2 * K2 + K2 + (size_t)K2 * K2 * 6 + 2 * (size_t)K2 * MIX_TB) * sizeof(float);
         dim3 mgrid(ceil_div(bins, MIX_TB), N);
@@ -585,17 +445,7 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
         SHGAN_LAUNCH_CHECK();
     }
 
-    ShuBands bands;
-    bands.num_bands = num_bands;
-    bands.lowest_log2 = log2low;
-    int off = 0;
-    for (int k = 0; k < num_bands; ++k) {
-        const int r = lowest_res << k;
-        SHGAN_CHECK(outs[k], "null output pointer");
-        bands.out[k] = outs[k];
-        bands.gauss_off[k] = off;
-        off += r * (r / 2 + 1);
-    }
+    if (fast64) return launch_shu_irfft2_r64(spec2, gauss, bands, N, C, stream);
     if (lowest_res <= 128) {
         int small_bands = 0;
         while (small_bands < num_bands && (lowest_res << small_bands) <= 128) ++small_bands;

@@ -29,7 +29,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert loaded.shgan_abi_version() == _lib.ABI_VERSION
     assert loaded.shgan_conv_num_nblocks(512, 0) == 16 and loaded.shgan_conv_num_nblocks(64, 0) == 2
     assert loaded.shgan_shu_workspace_bytes(2, 16, 64) == 2 * 2 * 32 * 64 * 33 * 4 + 256      # spec1 + spec2 (+ alignment slack)
-    assert loaded.shgan_shu_packed_bytes(32) == 7 * 2 * 64 * 72 * 2                            # 7 matrices, hi + lo, 72-half rows
+    assert loaded.shgan_shu_packed_bytes(32) == 16384 + 3 * 32768                               # swizzled conv0 + three anchor-pair operand tiles, hi + lo
     assert loaded.shgan_shu_workspace_bytes(2, 32, 64) > 2 * 2 * 64 * 64 * 33 * 4             # + tensor-core mix operands (C == 32)
     # struct layouts the binding assumes
     assert ctypes.sizeof(_lib.Epilogue) % 8 == 0 and ctypes.sizeof(_lib.ConvDesc) % 8 == 0
