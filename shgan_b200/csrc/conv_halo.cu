@@ -98,7 +98,6 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int BN>
 __global__ void __launch_bounds__(HL_THREADS, 1)

@@ -367,6 +367,7 @@ extern "C" int64_t shgan_shu_workspace_bytes(int N, int C, int R) {
     int64_t b = 2LL * N * 2 * C * bins * (int64_t)sizeof(float) + 256;            // spec1, spec2
     if (R > 128) b += (int64_t)N * C * bins * (int64_t)sizeof(float2);            // row/column pass scratch
     if (C == 32) b += shgan_shu_packed_bytes(C) + 256;                            // on-the-fly weight packing when none is passed
+    if (C == 32 && R == 64) b += 6 * bins * (int64_t)sizeof(float) + 256 + 8192;  // blend weights in the kx-major bin order (shu_fft64.cu) + trace
     return b;
 }
 
@@ -417,8 +418,9 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
         })) return e;
     const int Rs = R < 128 ? R : 128;       // size the single-CTA transforms see
     const size_t fft_smem_bytes = ((size_t)(Rs / 2) * Rs + (size_t)Rs * (Rs / 2 + 1) + Rs / 2) * sizeof(float2);
+    float* cw_kx = (float*)(((uintptr_t)extra + SHU_PACKED_BYTES + 255) & ~(uintptr_t)255);   // fast64 only (workspace sized for it)
     if (fast64) {
-        if (int e = launch_shu_rfft2_r64(x, spec1, N, C, stream)) return e;
+        if (int e = launch_shu_rfft2_r64(x, spec1, cw, cw_kx, N, C, stream)) return e;
     } else if (R <= 128) {
         shu_rfft2_kernel<<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, C, R, log2R);
         SHGAN_LAUNCH_CHECK();
@@ -437,7 +439,8 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
             packed = extra;
         }
         // |X_forward-normalised| <= max|x| <= 256 (lrelu_agc clamp): x R stays far below fp16 max for R <= 128; larger R use 128
-        if (int e = launch_shu_mix_tc(spec1, packed, conv0_b, cw, spec2, N, R, fast64 ? 1 : 0, (float)(R < 128 ? R : 128), stream)) return e;
+        if (int e = launch_shu_mix_tc(spec1, packed, conv0_b, fast64 ? cw_kx : cw, spec2, N, R, (float)(R < 128 ? R : 128), stream,
+                                      fast64 ? (void*)(cw_kx + 6 * bins) : nullptr /* cycle trace (development aid), see shu_workspace_bytes */)) return e;
     } else {
         const size_t mix_smem = ((size_t)K2 * K2 + K2 + (size_t)K2 * K2 * 6 + 2 * (size_t)K2 * MIX_TB) * sizeof(float);
         dim3 mgrid(ceil_div(bins, MIX_TB), N);

@@ -123,7 +123,8 @@ constexpr int F64_OFF_BAR = F64_OFF_ST + 2 * 2 * F64_BINS * 4;
 constexpr int F64_SMEM = F64_OFF_BAR + 16;
 
 __global__ void __launch_bounds__(F64_THREADS, 2)
-shu_rfft2_r64_kernel(const float* __restrict__ x, float* __restrict__ spec1, int planes, int C) {
+shu_rfft2_r64_kernel(const float* __restrict__ x, float* __restrict__ spec1, const float* __restrict__ cw, float* __restrict__ cw_kxmajor,
+                     int planes, int C) {
     extern __shared__ __align__(128) uint8_t sm[];
     float* xin = reinterpret_cast<float*>(sm);                          // [2][64][64]
     float2* zs = reinterpret_cast<float2*>(sm + F64_OFF_Z);             // [32][F64_ZP]
@@ -148,6 +149,13 @@ shu_rfft2_r64_kernel(const float* __restrict__ x, float* __restrict__ spec1, int
         mbar_fence_init();
     }
     __syncthreads();
+    // the blend weights of the channel mix in the bin order of the spectrum written here (kx-major), for the launch that follows
+    if (blockIdx.x == 0 && cw_kxmajor) {
+        for (int i = tid; i < 6 * F64_BINS; i += F64_THREADS) {
+            const int k6 = i / F64_BINS, e = i - k6 * F64_BINS;
+            cw_kxmajor[i] = __ldg(cw + k6 * F64_BINS + (e & 63) * 33 + (e >> 6));
+        }
+    }
     if (tid == 0) {
         for (int j = 0; j < 2; ++j) {
             const long long pl = (long long)blockIdx.x + (long long)j * gridDim.x;
@@ -230,9 +238,12 @@ shu_rfft2_r64_kernel(const float* __restrict__ x, float* __restrict__ spec1, int
 }
 
 // =============================================== inverse =====================================================================
-constexpr int I64_THREADS = 384;
+constexpr int I64_THREADS = 448;
 // thread ranges of the bands: (r/2 + 1) * M threads in the column stage, (r/2) * M in the row stage, M = max(r / 8, 1)
-constexpr int I64_B64 = 0, I64_B32 = 264, I64_B16 = 332, I64_B8 = 350, I64_B4 = 355, I64_END = 358;
+// band starts are warp-aligned so that no warp runs two long roles one after the other (its lanes would serialise them and every
+// other warp would wait for it at the block barrier): warp 8 holds the 33rd column transform of r = 64 only, r = 32 starts at
+// warp 9, r = 16 has warp 12, r = 8 and r = 4 (short roles) share warp 13
+constexpr int I64_B64 = 0, I64_B32 = 288, I64_B16 = 384, I64_B8 = 416, I64_B4 = 421, I64_END = 424;
 template <int r> struct InvBand {
     static constexpr int M = r >= 8 ? r / 8 : 1;
     static constexpr int RH = r / 2 + 1;
@@ -364,6 +375,7 @@ shu_irfft2_r64_kernel(const float* __restrict__ spec2, const float* __restrict__
     else if (tid < I64_B8) { lr = 4; lt = tid - I64_B16; }
     else if (tid < I64_B4) { lr = 3; lt = tid - I64_B8; }
     else if (tid < I64_END) { lr = 2; lt = tid - I64_B4; }
+    // (threads past a band's last transform fall out through col_on / row_on below)
     if (lr < bands.lowest_log2) lr = 0;                    // this band is not produced
     const int bi = lr - bands.lowest_log2;
     const float* gm = gauss + (lr ? bands.gauss_off[bi] : 0);
@@ -494,7 +506,7 @@ shu_irfft2_r64_kernel(const float* __restrict__ spec2, const float* __restrict__
 }
 
 // =============================================== host ========================================================================
-int launch_shu_rfft2_r64(const float* x, float* spec1, int N, int C, cudaStream_t stream) {
+int launch_shu_rfft2_r64(const float* x, float* spec1, const float* cw, float* cw_kxmajor, int N, int C, cudaStream_t stream) {
     static DeviceInit once;
     int num_sms = 148;
     if (int e = device_init(once, &num_sms, []() -> int {
@@ -504,7 +516,7 @@ int launch_shu_rfft2_r64(const float* x, float* spec1, int N, int C, cudaStream_
         })) return e;
     const int planes = N * C;
     const int grid = planes < 2 * num_sms ? planes : 2 * num_sms;
-    shu_rfft2_r64_kernel<<<grid, F64_THREADS, F64_SMEM, stream>>>(x, spec1, planes, C);
+    shu_rfft2_r64_kernel<<<grid, F64_THREADS, F64_SMEM, stream>>>(x, spec1, cw, cw_kxmajor, planes, C);
     SHGAN_LAUNCH_CHECK();
     return 0;
 }

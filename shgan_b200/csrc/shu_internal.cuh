@@ -17,13 +17,14 @@ struct ShuBands {
 //   nodes of width node p of the [2,3] heterogeneous filter): [pair hi 16 KB][pair lo 16 KB], rows 0..63 = W1_p, 64..127 = W1_{3+p}
 constexpr int SHU_PACKED_BYTES = 16384 + 3 * 32768;
 
-// spectra between the three kernels: [N, 2C, bins] fp32.  transposed == 0: bin = s * Rh + kx (row-shifted spectrum, row-major,
-// the layout of the generic-size transforms); transposed == 1: bin = kx * R + s (what shu_fft64.cu writes / reads)
-int launch_shu_mix_tc(const float* spec1, const void* packed, const float* conv0_b, const float* cw, float* spec2, int N, int R,
-                      int transposed, float scale, cudaStream_t stream);
+// spectra between the three kernels: [N, 2C, bins] fp32.  Generic-size transforms: bin = s * Rh + kx (row-shifted spectrum,
+// row-major); shu_fft64.cu: bin = kx * R + s (kx-major).  cw_binorder: the blend weights [6, bins] in that same bin order.
+int launch_shu_mix_tc(const float* spec1, const void* packed, const float* conv0_b, const float* cw_binorder, float* spec2, int N, int R,
+                      float scale, cudaStream_t stream, void* trace = nullptr);
 
 // input_res == 64, C == 32, lowest_res >= 4: spectra in the transposed layout
-int launch_shu_rfft2_r64(const float* x, float* spec1, int N, int C, cudaStream_t stream);
+// cw [6, 64, 33] -> cw_kxmajor [6, 33 * 64] is written by block 0 of the forward launch (consumed by the mix launch that follows)
+int launch_shu_rfft2_r64(const float* x, float* spec1, const float* cw, float* cw_kxmajor, int N, int C, cudaStream_t stream);
 int launch_shu_irfft2_r64(const float* spec2, const float* gauss, const ShuBands& bands, int N, int C, cudaStream_t stream);
 
 }  // namespace shgan
