@@ -106,7 +106,7 @@ conv_halo_kernel(const __grid_constant__ HaloTmaps maps, const ConvGeom g, const
     using Cfg = HaloCfg<BN>;
     constexpr int W_SLOTS = Cfg::W_SLOTS;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     const int a_plane = ti.a_px * 128;                    // multiple of 1024
     uint8_t* a_base = smem;                               // [buf][plane hi/lo][a_px][128 B]
     uint8_t* w_base = smem + 4 * a_plane;                 // [W_SLOTS][BN][128 B]

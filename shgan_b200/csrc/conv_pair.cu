@@ -139,7 +139,7 @@ conv_pair_kernel(const __grid_constant__ PairTmaps maps, const ConvGeom g, const
     using Cfg = PairCfg<BN>;
     constexpr int CP_BN = BN, CP_STAGES = Cfg::STAGES, CP_NACC = Cfg::NACC, CP_STAGE_BYTES = Cfg::STAGE_BYTES, CP_B_BYTES = Cfg::B_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CP_STAGES * CP_STAGE_BYTES);
     uint64_t* full_bar = bars;                           // [STAGES] (leader's are the live ones)
     uint64_t* empty_bar = bars + CP_STAGES;              // [STAGES]

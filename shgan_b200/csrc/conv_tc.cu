@@ -77,7 +77,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* full_bar = bars;                    // [STAGES] TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;          // [STAGES] MMA -> TMA

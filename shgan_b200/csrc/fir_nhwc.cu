@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
 fir4x4_tma_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__ f, float gain, int N, int C, int OH, int OW,
                   int pad_x0, int pad_y0, EpiParams epi, int parity_split, FirTiles ft, int skip_rank1) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * FT_STAGE_BYTES);
     __shared__ float s_f[FIR_T * FIR_T];
     if (threadIdx.x < FIR_T * FIR_T) s_f[threadIdx.x] = f[threadIdx.x] * gain;
@@ -325,7 +325,7 @@ fir4x4_tma_kernel(const __grid_constant__ FirMaps maps, const float* __restrict_
 // ncu on the kernels above (profiles/r1_fir_ncu_summary.txt): they are INSTRUCTION bound, not HBM bound -- 70 issued
 // instructions per output element at 8 warps per SM (16-tap 2-D filter, the hi/lo -> fp32 unpack repeated by each of the
 // 4 threads that touch a pixel, index arithmetic), 58 % issue utilisation, 2.4 TB/s.  This kernel needs ~25:
-//   * TMA stages a (32+3) x (12+3) pixel x 32 channel input window per tile, double buffered (as above);
+//   * TMA stages a (16+3) x (12+3) pixel x 32 channel input window per tile, double buffered (as above);
 //   * phase A, all 512 threads: horizontal 4-tap pass.  One item = 4 adjacent output pixels x 8 channels of one input
 //     row: 7 pixel vectors are unpacked once and give 32 results (1.75 unpacks per result instead of 4), written as
 //     fp32 to a shared-memory row buffer;
@@ -335,21 +335,26 @@ fir4x4_tma_kernel(const __grid_constant__ FirMaps maps, const float* __restrict_
 // f = u (x) v is factorised on the device (the filter is a device tensor in the C ABI) and verified to 1e-6 relative; when
 // it is not rank 1 this kernel returns immediately and the general kernels above, launched right after it, do the work
 // (and return immediately in the rank-1 case): no host synchronisation, CUDA-graph safe.
-constexpr int F2_W = 32, F2_H = 12, F2_C = 32;
-constexpr int F2_IW = F2_W + FIR_T - 1, F2_IH = F2_H + FIR_T - 1;      // 35 x 15
-constexpr int F2_THREADS = 512;
-constexpr int F2_PLANE_BYTES = F2_IH * F2_IW * F2_C * 2;               // 33600
+// Tile 16 x 12 pixels x 32 channels, 256 threads, TWO CTAs per SM (104 KB of shared memory each): the two block barriers per tile of
+// one CTA overlap the other CTA's passes (one 512-thread CTA per SM with 32-pixel-wide tiles measured 0.74 ms on the 64-channel
+// 512^2 layer, batch 16).
+constexpr int F2_W = 16, F2_H = 12, F2_C = 32;
+constexpr int F2_QBITS = 2;                                              // log2(F2_W / 4): pixel quads per tile row
+constexpr int F2_IW = F2_W + FIR_T - 1, F2_IH = F2_H + FIR_T - 1;      // 19 x 15
+static_assert((1 << F2_QBITS) * 4 == F2_W, "F2_QBITS must match F2_W");
+constexpr int F2_THREADS = 256;
+constexpr int F2_PLANE_BYTES = F2_IH * F2_IW * F2_C * 2;               // 18240
 constexpr int F2_PLANE_STRIDE = ((F2_PLANE_BYTES + 127) / 128) * 128;   // TMA destinations are 128 B aligned
 constexpr int F2_STAGE_BYTES = 2 * F2_PLANE_STRIDE;                    // hi + lo planes
-constexpr int F2_HBUF_BYTES = F2_IH * F2_W * F2_C * 4;                 // 61440
+constexpr int F2_HBUF_BYTES = F2_IH * F2_W * F2_C * 4;                 // 30720
 constexpr int F2_SMEM_BYTES = 2 * F2_STAGE_BYTES + F2_HBUF_BYTES + 128 + 64;
 static_assert((F2_H * F2_W * (F2_C / 4)) % F2_THREADS == 0, "phase B items must divide evenly over the threads");
 
-__global__ void __launch_bounds__(F2_THREADS, 1)
+__global__ void __launch_bounds__(F2_THREADS, 2)
 fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__ f, float gain, int N, int C, int OH, int OW,
                  int pad_x0, int pad_y0, EpiParams epi, int parity_split, FirTiles ft) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     float* hbuf = reinterpret_cast<float*>(smem + 2 * F2_STAGE_BYTES);             // [F2_IH][F2_W][F2_C]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * F2_STAGE_BYTES + F2_HBUF_BYTES);
     __shared__ float s_f[FIR_T * FIR_T];
@@ -402,7 +407,7 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
         // ---------------- phase A: horizontal pass -> hbuf ----------------
 #pragma unroll 1
         for (int item = threadIdx.x; item < ((F2_IH + 1) / 2) * 2 * (F2_W / 4) * (F2_C / 8); item += F2_THREADS) {
-            const int cg = item & 3, rs = (item >> 2) & 1, q = (item >> 3) & 7, r = ((item >> 6) << 1) | rs;
+            const int cg = item & 3, rs = (item >> 2) & 1, q = (item >> 3) & (F2_W / 4 - 1), r = ((item >> (3 + F2_QBITS)) << 1) | rs;
             if (r >= F2_IH) continue;
             float row[FIR_T + 3][8];
 #pragma unroll
@@ -552,7 +557,7 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
         const uint32_t box[4] = {(uint32_t)F2_C, (uint32_t)F2_IW, (uint32_t)F2_IH, 1u};
         if (int e = encode_tmap(&maps.a, in_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
         if (int e = encode_tmap(&maps.b, in_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, dims, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
-        const int grid = ft.total < num_sms ? ft.total : num_sms;
+        const int grid = ft.total < 2 * num_sms ? ft.total : 2 * num_sms;
         fir4x4_2p_kernel<<<grid, F2_THREADS, F2_SMEM_BYTES, (cudaStream_t)stream>>>(maps, f, gain, N, C, OH, OW, pad_x0, pad_y0, epi,
                                                                                   parity_split, ft);
         SHGAN_LAUNCH_CHECK();
