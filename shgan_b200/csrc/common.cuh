@@ -144,17 +144,22 @@ __device__ __forceinline__ void load_planes8(const __half* __restrict__ hi, cons
     }
 }
 
+// two values -> one packed word of each plane.  Packed conversions (F2FP.PACK_AB, two results per instruction) instead of four
+// scalar F2F per pair: same round-to-nearest results bit for bit, half the instructions on the conversion pipe (the scalar
+// form was a third of fromrgb's issue slots and sits in every convolution / FIR epilogue).
+__device__ __forceinline__ void split2_f32(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 f2 = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a - f2.x, b - f2.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
 __device__ __forceinline__ void store_planes8(__half* __restrict__ hi, __half* __restrict__ lo, long long idx,
                                               const float* v) {
     uint32_t hw[4], lw[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __half h0, l0, h1, l1;
-        split_f32(v[2 * i], h0, l0);
-        split_f32(v[2 * i + 1], h1, l1);
-        hw[i] = pack_h2(h0, h1);
-        lw[i] = pack_h2(l0, l1);
-    }
+    for (int i = 0; i < 4; ++i) split2_f32(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
     *reinterpret_cast<uint4*>(hi + idx) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     *reinterpret_cast<uint4*>(lo + idx) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
@@ -164,13 +169,7 @@ __device__ __forceinline__ void store_planes8(__half* __restrict__ hi, __half* _
 __device__ __forceinline__ void store_planes16(__half* __restrict__ hi, __half* __restrict__ lo, long long idx, const float* v) {
     uint32_t hw[8], lw[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        __half h0, l0, h1, l1;
-        split_f32(v[2 * i], h0, l0);
-        split_f32(v[2 * i + 1], h1, l1);
-        hw[i] = pack_h2(h0, h1);
-        lw[i] = pack_h2(l0, l1);
-    }
+    for (int i = 0; i < 8; ++i) split2_f32(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(hi + idx), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]),
                  "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7]) : "memory");
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(lo + idx), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]),

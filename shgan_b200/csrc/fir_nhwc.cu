@@ -498,11 +498,11 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
                     const size_t oidx = (size_t)(out_pix * C + c0);
                     if (epi.out_f32) *reinterpret_cast<float4*>(epi.out_f32 + oidx) = make_float4(o[0], o[1], o[2], o[3]);
                     if (epi.out_hi) {
-                        __half hh[4], ll[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) split_f32(o[j] * e_nx[j], hh[j], ll[j]);
-                        *reinterpret_cast<uint2*>(epi.out_hi + oidx) = make_uint2(pack_h2(hh[0], hh[1]), pack_h2(hh[2], hh[3]));
-                        *reinterpret_cast<uint2*>(epi.out_lo + oidx) = make_uint2(pack_h2(ll[0], ll[1]), pack_h2(ll[2], ll[3]));
+                        uint32_t h01, l01, h23, l23;
+                        split2_f32(o[0] * e_nx[0], o[1] * e_nx[1], h01, l01);
+                        split2_f32(o[2] * e_nx[2], o[3] * e_nx[3], h23, l23);
+                        *reinterpret_cast<uint2*>(epi.out_hi + oidx) = make_uint2(h01, h23);
+                        *reinterpret_cast<uint2*>(epi.out_lo + oidx) = make_uint2(l01, l23);
                     }
                 }
             }

@@ -26,14 +26,30 @@ fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ mask, floa
     for (int i = threadIdx.x; i < Co * Ci; i += blockDim.x) s_w[(i % Ci) * Co + i / Ci] = w[i] * wgain;
     for (int i = threadIdx.x; i < Co; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const int cgs = Co / 8;
-    const long long total = (long long)N * HW * cgs;
-    for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
-         gid += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(gid % cgs);
-        const long long pix = gid / cgs;           // n*HW + p
-        const int n = (int)(pix / HW);
-        const int p = (int)(pix - (long long)n * HW);
+    // 32-bit index arithmetic without divisions in the loop (the host checks N*Co*H*W <= INT32_MAX; 64-bit modulo / division per
+    // element were ~half of this kernel's instructions): the channel group of a thread is loop invariant when the grid stride is
+    // a multiple of the groups per pixel, and (n, p) advance incrementally
+    const unsigned cgs = (unsigned)Co / 8u, total_pix = (unsigned)N * (unsigned)HW;
+    const unsigned gstride = gridDim.x * blockDim.x;
+    const bool inv = gstride % cgs == 0;
+    const unsigned gid0 = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned pix_u = gid0 / cgs, cg_u = gid0 - pix_u * cgs;
+    unsigned n_u = pix_u / (unsigned)HW, p_u = pix_u - n_u * (unsigned)HW;
+    const unsigned pstride = gstride / cgs;
+    for (unsigned gid = gid0; pix_u < total_pix; gid += gstride) {
+        const int cg = (int)cg_u, n = (int)n_u, p = (int)p_u;
+        const long long pix = (long long)pix_u;    // n*HW + p
+        if (inv) {
+            pix_u += pstride;
+            p_u += pstride;
+            while (p_u >= (unsigned)HW) { p_u -= (unsigned)HW; ++n_u; }
+        } else {
+            const unsigned g2 = gid + gstride;
+            pix_u = g2 < gid ? total_pix : g2 / cgs;   // (overflow guard)
+            cg_u = g2 - pix_u * cgs;
+            n_u = pix_u / (unsigned)HW;
+            p_u = pix_u - n_u * (unsigned)HW;
+        }
         float xin[FRGB_MAX_CI];
         if (mask) {
             const float m = __ldg(mask + (long long)n * HW + p);

@@ -287,6 +287,73 @@ def test_shu_narrow_uses_fma_mix():
         assert relerr(y[r].cpu().numpy(), ref[r]) <= 2e-5, r
 
 
+def _shu_numpy(x, conv0_w, conv0_b, df1_w, cw, masks, r):
+    """float64 restatement of SHU.forward (shgan.py:312-336) for arbitrary cw / Gaussian masks (numpy pocketfft)."""
+    n = x.shape[0]
+    f = np.fft.rfft2(x.astype(np.float64), norm='forward')
+    f = np.concatenate([f[:, :, r // 2 + 1:], f[:, :, :r // 2 + 1]], axis=2)
+    s1 = np.concatenate([f.real, f.imag], axis=1)
+    tt = np.maximum(np.einsum('oi,nisk->nosk', conv0_w.astype(np.float64), s1) + conv0_b.astype(np.float64)[None, :, None, None], 0)
+    y = np.einsum('io,nisk->nosk', df1_w.astype(np.float64), tt).reshape(n, 64, 6, r, r // 2 + 1)
+    s2 = (y * cw.astype(np.float64)[None, None]).sum(2)
+    fc = s2[:, :32] + 1j * s2[:, 32:]
+    out = {}
+    for k, mk in masks.items():
+        sp = fc[:, :, r // 2 - k // 2:r // 2 + k // 2, :k // 2 + 1] * mk.astype(np.float64)[None, None]
+        sp = np.concatenate([sp[:, :, k - k // 2 - 1:], sp[:, :, :k - k // 2 - 1]], axis=2)
+        out[k] = np.fft.irfft2(sp, s=(k, k), norm='forward')
+    return out
+
+
+@pytest.mark.parametrize('lowest,dense_cw,prepacked', [(4, False, True), (8, False, False), (16, True, True), (64, True, False)])
+def test_shu_r64_register_fft_path(lowest, dense_cw, prepacked):
+    """input_res 64 (the released model): register-resident radix-8 transforms + tcgen05 channel mix (shu_fft64.cu,
+    shu_mix_tc.cu) through the C ABI, against float64 numpy: every lowest_res (bands that are not produced), a cw with all six
+    anchors active everywhere (three anchor pairs per tile instead of two), random Gaussian masks, weights packed per call."""
+    from shgan_b200 import kernels as K, packing as P
+    g = rng(900 + lowest)
+    r, n = 64, 5
+    conv0_w = (g.standard_normal((64, 64)) / 8).astype(np.float32)
+    conv0_b = (0.1 * g.standard_normal(64)).astype(np.float32)
+    df1_w = (1 / 64 + 0.1 / 64 * g.standard_normal((64, 384))).astype(np.float32)
+    cw = g.uniform(0.1, 1.0, (6, r, r // 2 + 1)).astype(np.float32) if dense_cw else P.make_cweight((2, 3), (r, r // 2 + 1)).numpy()
+    reslist = [k for k in (4, 8, 16, 32, 64) if k >= lowest]
+    masks = {k: g.uniform(0.2, 1.0, (k, k // 2 + 1)).astype(np.float32) for k in reslist}
+    x = g.standard_normal((n, 32, r, r)).astype(np.float32)
+    gauss = np.concatenate([masks[k].reshape(-1) for k in reslist])
+    outs = [torch.empty(n, 32, k, k, device=DEV) for k in reslist]
+    packed = K.shu_pack(t(conv0_w), t(df1_w)) if prepacked else None
+    K.shu_fwd(t(x), t(conv0_w), t(conv0_b), t(df1_w), t(cw), t(gauss), outs, lowest, packed=packed)
+    ref = _shu_numpy(x, conv0_w, conv0_b, df1_w, cw, masks, r)
+    for o, k in zip(outs, reslist):
+        assert relerr(o.cpu().numpy(), ref[k]) <= 2e-5, k
+
+
+def test_shu_r64_unaligned_input_falls_back():
+    """The bulk copies of the register-FFT path need 16-byte aligned planes; an x that is only 4-byte aligned takes the generic
+    shared-memory transforms (row-major spectrum) with the same results."""
+    from shgan_b200 import kernels as K, packing as P
+    g = rng(77)
+    r, n = 64, 2
+    conv0_w = (g.standard_normal((64, 64)) / 8).astype(np.float32)
+    conv0_b = (0.1 * g.standard_normal(64)).astype(np.float32)
+    df1_w = (1 / 64 + 0.1 / 64 * g.standard_normal((64, 384))).astype(np.float32)
+    cw = P.make_cweight((2, 3), (r, r // 2 + 1)).numpy()
+    mk = {k: v.numpy() for k, v in P.gaussian_band_masks(r, 4, 3, False).items()}
+    reslist = sorted(mk)
+    x = g.standard_normal((n, 32, r, r)).astype(np.float32)
+    buf = torch.empty(x.size + 1, device=DEV)
+    xd = buf[1:].view(n, 32, r, r)
+    xd.copy_(t(x))
+    assert xd.data_ptr() % 16 == 4
+    gauss = np.concatenate([mk[k].reshape(-1) for k in reslist])
+    outs = [torch.empty(n, 32, k, k, device=DEV) for k in reslist]
+    K.shu_fwd(xd, t(conv0_w), t(conv0_b), t(df1_w), t(cw), t(gauss), outs, 4)
+    ref = _shu_numpy(x, conv0_w, conv0_b, df1_w, cw, mk, r)
+    for o, k in zip(outs, reslist):
+        assert relerr(o.cpu().numpy(), ref[k]) <= 2e-5, k
+
+
 def test_fir_decimate_and_mbstd():
     from shgan_b200 import kernels as K
     r = np.random.default_rng(8)
