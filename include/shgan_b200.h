@@ -266,9 +266,13 @@ int shgan_style_prep_batched(const float* raw, int64_t raw_stride, int N, const 
  * conv0_w [2C,2C], conv0_b [2C], df1_w [2C, 2C*6] (reference parameter layouts),
  * cw [6,R,R/2+1] and the Gaussian band masks gauss[r] ([r, r/2+1], r = lowest_res..R, concatenated
  * lowest band first) are the constants of shgan.py:70-121,280-310.
- * packed_w: the fp16 hi/lo operands of the tensor-core channel mix (C == 32), written ONCE per parameter set by
- *   shgan_shu_pack into a buffer of shgan_shu_packed_bytes(C) bytes; NULL = pack into the workspace on every call.
- * spec_ws: workspace of shgan_shu_workspace_bytes(N,C,R) bytes.
+ * packed_w: the fp16 hi/lo operands of the tensor-core channel mix (C == 32) as the kernel's pre-swizzled shared-memory
+ *   image, written ONCE per parameter set by shgan_shu_pack into a 16-byte aligned buffer of shgan_shu_packed_bytes(C)
+ *   bytes; NULL = pack into the workspace on every call.
+ * spec_ws: 16-byte aligned workspace of shgan_shu_workspace_bytes(N,C,R) bytes (the two spectra, scratch for R > 128, and
+ *   for R == 64 the blend weights in the spectrum's bin order).
+ * R == 64, C == 32, lowest_res >= 4 with x and every outs[k] 16-byte aligned runs the register-resident radix-8 transforms
+ *   (whole planes move by bulk copies); any other case runs the generic shared-memory transforms, same results.
  * outs[k] -> [N,C,r_k,r_k] fp32 for r_k = lowest_res * 2^k. */
 int64_t shgan_shu_packed_bytes(int C);
 int shgan_shu_pack(const float* conv0_w, const float* df1_w, void* packed, int C, void* stream);
