@@ -75,7 +75,9 @@ __device__ __forceinline__ void make_tw(float2 (&tw)[8], int S, int t, int rin, 
 }
 
 // scratch of one transform group: [c = 0..7][b = 0..M-1] at a pitch of M + 1 float2
-template <int M> struct FftScratch { static constexpr int PITCH = M + 1, SIZE = 8 * (M + 1); };
+// and the groups of a warp at a pitch that spreads them over the banks (72 / 52 / 34 float2 for M = 8 / 4 / 2: the 16 lanes
+// of a half-warp -- 2 / 4 / 8 groups -- then touch 16 distinct bank pairs in both the column-of-scratch writes and the row reads)
+template <int M> struct FftScratch { static constexpr int PITCH = M + 1, SIZE = M == 8 ? 72 : (M == 4 ? 52 : (M == 2 ? 34 : 16)); };
 
 // In: v[a] = x[t + M ((a + rin) & 7)].  Out: v[q] = X[t + M e + 8 ((d + rout) % M)], q = e + (8 / M) d.
 template <int M, int S>
@@ -247,7 +249,7 @@ constexpr int I64_B64 = 0, I64_B32 = 288, I64_B16 = 384, I64_B8 = 416, I64_B4 = 
 template <int r> struct InvBand {
     static constexpr int M = r >= 8 ? r / 8 : 1;
     static constexpr int RH = r / 2 + 1;
-    static constexpr int ZP = r + 2;                          // float2 pitch of Zrow[pair][k]
+    static constexpr int ZP = r == 64 ? 66 : (r == 32 ? 36 : (r == 16 ? 20 : r + 2));   // float2 pitch of Zrow[pair][k] (bank spreading)
     static constexpr int NCOL = RH * M, NROW = (r / 2) * M;
     static constexpr int ZROW_F2 = (r / 2) * ZP;
     static constexpr int EX_F2 = RH * FftScratch<M>::SIZE;

@@ -70,6 +70,14 @@ def test_sass_has_tcgen05_and_tma():
         assert mnemonic in pair, mnemonic
     halo = subprocess.run([cuobjdump, '-sass', os.path.join(os.path.dirname(obj), 'conv_halo.o')], capture_output=True, text=True).stdout
     assert 'UTCHMMA' in halo and 'BRA.U.ANY' not in halo
+    # the SHU: tcgen05 channel mix with bulk-copied weight image, no generic shared-memory accesses, no scalar conversions;
+    # register-FFT kernels moving whole planes with bulk copies, their shared-memory traffic as LDS / STS
+    mix = subprocess.run([cuobjdump, '-sass', os.path.join(os.path.dirname(obj), 'shu_mix_tc.o')], capture_output=True, text=True).stdout
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP', 'F2FP'):
+        assert mnemonic in mix, mnemonic
+    assert 'LD.E.128' not in mix and 'ST.E.128' not in mix and 'F2F.F16.F32' not in mix and 'BRA.U.ANY' not in mix
+    fft = subprocess.run([cuobjdump, '-sass', os.path.join(os.path.dirname(obj), 'shu_fft64.o')], capture_output=True, text=True).stdout
+    assert 'UBLKCP' in fft and 'LDS' in fft and 'STS' in fft and 'ST.E.64' not in fft
 
 
 def test_product_library_has_no_cuda_core_convolution():
