@@ -65,41 +65,46 @@ __device__ __forceinline__ void fill_twiddles(float2* tw, int Lmax) {
 }
 
 // ---- 1. forward rfft2 ------------------------------------------------------------------------
-// grid (N*C), dynamic smem: rowbuf [R/2][R] + colbuf [R][Rh] + tw [R/2] float2
+// grid ceil(N*C / P): P planes per CTA (small planes: more work per block barrier of the radix-2 stages);
+// dynamic smem: rowbuf [P][R/2][R] + colbuf [R][P][Rh] (planes interleaved per row: the P * Rh column transforms of a CTA are
+// then one uniformly strided batch) + tw [R/2] float2
+template <bool MULTI>
 __global__ void __launch_bounds__(256)
-shu_rfft2_kernel(const float* __restrict__ x, float* __restrict__ spec1, int C, int R, int log2R) {
+shu_rfft2_kernel(const float* __restrict__ x, float* __restrict__ spec1, int NC, int C, int R, int log2R, int P_) {
     extern __shared__ float2 sm[];
-    const int Rh = R / 2 + 1;
+    const int P = MULTI ? P_ : 1;          // MULTI == false: one plane per CTA, the plane index below folds to 0 at compile time
+    const int Rh = R / 2 + 1, RR = (R / 2) * R, RC = R * Rh;
     float2* rowbuf = sm;
-    float2* colbuf = rowbuf + (R / 2) * R;
-    float2* tw = colbuf + R * Rh;
-    const int n = blockIdx.x / C, c = blockIdx.x % C;
-    const float* xp = x + (long long)blockIdx.x * R * R;
+    float2* colbuf = rowbuf + P * RR;
+    float2* tw = colbuf + P * RC;
+    const int plane0 = blockIdx.x * P;
+    const int np = NC - plane0 < P ? NC - plane0 : P;          // planes of this CTA
+    const float* xp = x + (long long)plane0 * R * R;
     fill_twiddles(tw, R);
-    for (int i = threadIdx.x; i < (R / 2) * R; i += blockDim.x) {
-        const int p = i / R, xx = i - p * R;
-        rowbuf[p * R + brev(xx, log2R)] = make_float2(__ldg(xp + (2 * p) * R + xx), __ldg(xp + (2 * p + 1) * R + xx));
+    for (int i = threadIdx.x; i < np * RR; i += blockDim.x) {
+        const int pl = MULTI ? i / RR : 0, r = i - pl * RR, p = r / R, xx = r - p * R;
+        const float* xq = xp + (long long)pl * R * R;
+        rowbuf[pl * RR + p * R + brev(xx, log2R)] = make_float2(__ldg(xq + (2 * p) * R + xx), __ldg(xq + (2 * p + 1) * R + xx));
     }
     __syncthreads();
-    fft_smem(rowbuf, log2R, R / 2, 1, R, -1.f, tw, log2R);
+    fft_smem(rowbuf, log2R, np * (R / 2), 1, R, -1.f, tw, log2R);
     // untangle the two real rows of each packed transform; store rows bit-reversed for the column pass
-    for (int i = threadIdx.x; i < (R / 2) * Rh; i += blockDim.x) {
-        const int p = i / Rh, k = i - p * Rh;
-        const float2 z = rowbuf[p * R + k], zz = rowbuf[p * R + ((R - k) & (R - 1))];
-        colbuf[brev(2 * p, log2R) * Rh + k] = make_float2(0.5f * (z.x + zz.x), 0.5f * (z.y - zz.y));
-        colbuf[brev(2 * p + 1, log2R) * Rh + k] = make_float2(0.5f * (z.y + zz.y), -0.5f * (z.x - zz.x));
+    for (int i = threadIdx.x; i < np * (R / 2) * Rh; i += blockDim.x) {
+        const int pl = MULTI ? i / ((R / 2) * Rh) : 0, r = i - pl * (R / 2) * Rh, p = r / Rh, k = r - p * Rh;
+        const float2 z = rowbuf[pl * RR + p * R + k], zz = rowbuf[pl * RR + p * R + ((R - k) & (R - 1))];
+        colbuf[(brev(2 * p, log2R) * P + pl) * Rh + k] = make_float2(0.5f * (z.x + zz.x), 0.5f * (z.y - zz.y));
+        colbuf[(brev(2 * p + 1, log2R) * P + pl) * Rh + k] = make_float2(0.5f * (z.y + zz.y), -0.5f * (z.x - zz.x));
     }
     __syncthreads();
-    fft_smem(colbuf, log2R, Rh, Rh, 1, -1.f, tw, log2R);
+    fft_smem(colbuf, log2R, P * Rh, P * Rh, 1, -1.f, tw, log2R);
     // norm='forward' scaling and the row shift of shgan.py:315-317: out row j holds X[(j + R/2 + 1) mod R]
     const float sc = 1.f / ((float)R * (float)R);
-    float* re = spec1 + ((long long)n * 2 * C + c) * R * Rh;
-    float* im = spec1 + ((long long)n * 2 * C + C + c) * R * Rh;
-    for (int i = threadIdx.x; i < R * Rh; i += blockDim.x) {
-        const int j = i / Rh, k = i - j * Rh;
-        const float2 v = colbuf[((j + R / 2 + 1) & (R - 1)) * Rh + k];
-        re[i] = v.x * sc;
-        im[i] = v.y * sc;
+    for (int i = threadIdx.x; i < np * RC; i += blockDim.x) {
+        const int pl = MULTI ? i / RC : 0, r = i - pl * RC, j = r / Rh, k = r - j * Rh;
+        const int plane = plane0 + pl, n = plane / C, c = plane - n * C;
+        const float2 v = colbuf[(((j + R / 2 + 1) & (R - 1)) * P + pl) * Rh + k];
+        spec1[((long long)n * 2 * C + c) * RC + r] = v.x * sc;
+        spec1[((long long)n * 2 * C + C + c) * RC + r] = v.y * sc;
     }
 }
 
@@ -177,49 +182,57 @@ shu_mix_kernel(const float* __restrict__ spec1, const float* __restrict__ conv0_
 
 // ---- 3. per-band inverse rfft2 -----------------------------------------------------------------
 
-// grid (N*C, num_bands); dynamic smem sized for the largest band: colbuf [r][rh] + rowbuf [r/2][r] + tw [R/2]
+// grid (ceil(N*C / P), num_bands), P planes per CTA; dynamic smem sized for the largest band: colbuf [r][P][rh] + rowbuf [P][r/2][r] + tw [R/2]
+template <bool MULTI>
 __global__ void __launch_bounds__(256)
-shu_irfft2_kernel(const float* __restrict__ spec2, const float* __restrict__ gauss, ShuBands bands, int C, int R, int log2R) {
+shu_irfft2_kernel(const float* __restrict__ spec2, const float* __restrict__ gauss, ShuBands bands, int NC, int C, int R, int log2R, int P_) {
     extern __shared__ float2 sm[];
+    const int P = MULTI ? P_ : 1;
     const int band = blockIdx.y;
     const int log2r = bands.lowest_log2 + band;
-    const int r = 1 << log2r, rh = r / 2 + 1, Rh = R / 2 + 1;
+    const int r = 1 << log2r, rh = r / 2 + 1, Rh = R / 2 + 1, rc = r * rh, rr = (r / 2) * r;
     if (r > 128) return;      // large bands run as a column pass + a row pass through global memory
     float2* colbuf = sm;
-    float2* rowbuf = colbuf + r * rh;
-    float2* tw = rowbuf + (r / 2) * r;
-    const int n = blockIdx.x / C, c = blockIdx.x % C;
-    const float* re = spec2 + ((long long)n * 2 * C + c) * R * Rh;
-    const float* im = spec2 + ((long long)n * 2 * C + C + c) * R * Rh;
+    float2* rowbuf = colbuf + P * rc;
+    float2* tw = rowbuf + P * rr;
+    const int plane0 = blockIdx.x * P;
+    const int np = NC - plane0 < P ? NC - plane0 : P;
     const float* gm = gauss + bands.gauss_off[band];
     fill_twiddles(tw, r);
     // crop rows [R/2 - r/2, R/2 + r/2), cols [0, rh) (shgan.py:328), mask (:329), un-shift rows (:331-333):
     // un-shifted row j holds cropped row (j + r/2 - 1) mod r
-    for (int i = threadIdx.x; i < r * rh; i += blockDim.x) {
-        const int j = i / rh, k = i - j * rh;
+    for (int i = threadIdx.x; i < np * rc; i += blockDim.x) {
+        const int pl = MULTI ? i / rc : 0, q = i - pl * rc, j = q / rh, k = q - j * rh;
+        const int plane = plane0 + pl, n = plane / C, c = plane - n * C;
+        const float* re = spec2 + ((long long)n * 2 * C + c) * R * Rh;
+        const float* im = spec2 + ((long long)n * 2 * C + C + c) * R * Rh;
         const int cj = (j + r / 2 - 1) & (r - 1);
         const int src = (R / 2 - r / 2 + cj) * Rh + k;
         const float g = __ldg(gm + cj * rh + k);
-        colbuf[brev(j, log2r) * rh + k] = make_float2(__ldg(re + src) * g, __ldg(im + src) * g);
+        colbuf[(brev(j, log2r) * P + pl) * rh + k] = make_float2(__ldg(re + src) * g, __ldg(im + src) * g);
+    }
+    for (int i = threadIdx.x + np * rc; i < P * rc; i += blockDim.x) {      // planes past the end of the batch: zeros
+        const int pl = i / rc, q = i - pl * rc;
+        colbuf[((q / rh) * P + pl) * rh + (q % rh)] = make_float2(0.f, 0.f);
     }
     __syncthreads();
-    fft_smem(colbuf, log2r, rh, rh, 1, +1.f, tw, log2r);
+    fft_smem(colbuf, log2r, P * rh, P * rh, 1, +1.f, tw, log2r);
     // Hermitian extension along the last axis (imaginary parts of the DC and Nyquist bins dropped),
     // rows 2p and 2p+1 packed as real and imaginary part of one complex inverse transform
-    for (int i = threadIdx.x; i < (r / 2) * r; i += blockDim.x) {
-        const int p = i / r, k = i - p * r;
+    for (int i = threadIdx.x; i < np * rr; i += blockDim.x) {
+        const int pl = MULTI ? i / rr : 0, q = i - pl * rr, p = q / r, k = q - p * r;
         const int kk = k <= r / 2 ? k : r - k;
-        float2 ya = colbuf[(2 * p) * rh + kk], yb = colbuf[(2 * p + 1) * rh + kk];
+        float2 ya = colbuf[((2 * p) * P + pl) * rh + kk], yb = colbuf[((2 * p + 1) * P + pl) * rh + kk];
         if (k > r / 2) { ya.y = -ya.y; yb.y = -yb.y; }
         if (k == 0 || k == r / 2) { ya.y = 0.f; yb.y = 0.f; }
-        rowbuf[p * r + brev(k, log2r)] = make_float2(ya.x - yb.y, ya.y + yb.x);
+        rowbuf[pl * rr + p * r + brev(k, log2r)] = make_float2(ya.x - yb.y, ya.y + yb.x);
     }
     __syncthreads();
-    fft_smem(rowbuf, log2r, r / 2, 1, r, +1.f, tw, log2r);
-    float* op = bands.out[band] + (long long)blockIdx.x * r * r;
-    for (int i = threadIdx.x; i < r * r; i += blockDim.x) {
-        const int j = i / r, xx = i - j * r;
-        const float2 v = rowbuf[(j >> 1) * r + xx];
+    fft_smem(rowbuf, log2r, np * (r / 2), 1, r, +1.f, tw, log2r);
+    float* op = bands.out[band] + (long long)plane0 * r * r;
+    for (int i = threadIdx.x; i < np * r * r; i += blockDim.x) {
+        const int pl = MULTI ? i / (r * r) : 0, q = i - pl * r * r, j = q / r, xx = q - j * r;
+        const float2 v = rowbuf[pl * rr + (j >> 1) * r + xx];
         op[i] = (j & 1) ? v.y : v.x;
     }
 }
@@ -411,18 +424,26 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     static DeviceInit once;
     int num_sms = 148;
     if (int e = device_init(once, &num_sms, []() -> int {
-            SHGAN_CUDA(cudaFuncSetAttribute(shu_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            SHGAN_CUDA(cudaFuncSetAttribute(shu_irfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            SHGAN_CUDA(cudaFuncSetAttribute(shu_rfft2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            SHGAN_CUDA(cudaFuncSetAttribute(shu_irfft2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            SHGAN_CUDA(cudaFuncSetAttribute(shu_rfft2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            SHGAN_CUDA(cudaFuncSetAttribute(shu_irfft2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             SHGAN_CUDA(cudaFuncSetAttribute(shu_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             return 0;
         })) return e;
     const int Rs = R < 128 ? R : 128;       // size the single-CTA transforms see
     const size_t fft_smem_bytes = ((size_t)(Rs / 2) * Rs + (size_t)Rs * (Rs / 2 + 1) + Rs / 2) * sizeof(float2);
+    // planes per CTA of the generic single-CTA transforms: small planes share a CTA (more work per block barrier of the radix-2
+    // stages; measured at batch 4096: input_res 4 / 8 / 16 0.78 / 1.31 / 2.12 -> 0.17 / 0.30 / 0.94 ms, no gain at 32 and a loss at
+    // 128 from the extra index arithmetic, hence R <= 16), as long as every SM still gets CTAs
+    int fft_planes = 1;
+    while (R <= 16 && fft_planes < 16 && (size_t)(2 * fft_planes) * fft_smem_bytes <= 40 * 1024 && (long long)N * C >= 2LL * num_sms * 2 * fft_planes) fft_planes *= 2;
     float* cw_kx = (float*)(((uintptr_t)extra + SHU_PACKED_BYTES + 255) & ~(uintptr_t)255);   // fast64 only (workspace sized for it)
     if (fast64) {
         if (int e = launch_shu_rfft2_r64(x, spec1, cw, cw_kx, N, C, stream)) return e;
     } else if (R <= 128) {
-        shu_rfft2_kernel<<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, C, R, log2R);
+        if (fft_planes > 1) shu_rfft2_kernel<true><<<ceil_div(N * C, fft_planes), 256, fft_planes * fft_smem_bytes, stream>>>(x, spec1, N * C, C, R, log2R, fft_planes);
+        else shu_rfft2_kernel<false><<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, N * C, C, R, log2R, 1);
         SHGAN_LAUNCH_CHECK();
     } else {
         const size_t sm_rows = ((size_t)BIG_RP * R + R / 2) * sizeof(float2), sm_cols = ((size_t)R * BIG_CB + R / 2) * sizeof(float2);
@@ -452,8 +473,9 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     if (lowest_res <= 128) {
         int small_bands = 0;
         while (small_bands < num_bands && (lowest_res << small_bands) <= 128) ++small_bands;
-        dim3 igrid(N * C, small_bands);
-        shu_irfft2_kernel<<<igrid, 256, fft_smem_bytes, stream>>>(spec2, gauss, bands, C, R, log2R);
+        dim3 igrid(ceil_div(N * C, fft_planes), small_bands);
+        if (fft_planes > 1) shu_irfft2_kernel<true><<<igrid, 256, fft_planes * fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, fft_planes);
+        else shu_irfft2_kernel<false><<<igrid, 256, fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, 1);
         SHGAN_LAUNCH_CHECK();
     }
     for (int k = 0; k < num_bands; ++k) {
