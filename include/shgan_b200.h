@@ -115,7 +115,11 @@ typedef struct {
  * z[n, oy*zsy+zoy, ox*zsx+zox, o] of a [N,ZH,ZW,Co] tensor (used by the 4 parity passes of the
  * stride-2 transposed convolution).  C and Co must be multiples of 64.  In ACT mode with rgb_w set, the
  * torgb partial sums of each block of 32 output channels are written to
- * rgb_out[n,y,x,blk,0..2] (blk < shgan_conv_num_nblocks); shgan_torgb_combine adds them up. */
+ * rgb_out[n,y,x,blk,0..2] (blk < shgan_conv_num_nblocks); shgan_torgb_combine adds them up.
+ * ACT mode with z != NULL: z is an optional split-K scratch of ZH >= 2 buffers of ZW >= N*OH*OW*Co floats (16-byte aligned).
+ * Layers with too few output tiles to fill the GPU (4x4 / 8x8) are then computed by several CTAs per tile, each over a slice of
+ * the (tap, channel) loop, their fp32 partials summed in a fixed order by a second launch that applies `epi`; any other layer
+ * ignores the scratch.  Results are deterministic and agree with the un-split launch to fp32 rounding. */
 typedef struct {
     int num_src;
     const void* src_hi[SHGAN_MAX_SRC];

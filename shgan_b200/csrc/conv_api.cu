@@ -43,6 +43,13 @@ extern "C" int shgan_conv_igemm(const shgan_conv_desc* d, void* stream_) {
     SHGAN_CHECK(d->impl != 1, "impl 1 (fp32 FMA cross-check) is not in the product library: it lives in the test-only libshgan_b200_check.so");
     SHGAN_CHECK(d->impl == 0 || (d->impl >= 2 && d->impl <= 4), "impl must be 0, 1, 2, 3 or 4");
     const int passes = d->passes == 0 ? 3 : d->passes;
+    // ACT mode with a scratch (z = ZH partial buffers of ZW floats): split-K for layers with too few tiles to fill the GPU
+    if (d->mode == 0 && d->z && d->impl == 0 && bn == 0 && !conv_prefers_pair(g)) {
+        SHGAN_CHECK(d->ZH >= 2 && (long long)d->ZW >= (long long)d->N * d->OH * d->OW * d->Co, "split-K scratch: z must hold ZH >= 2 buffers of ZW >= N*OH*OW*Co floats");
+        SHGAN_CHECK(((uintptr_t)d->z & 15) == 0 && (d->ZW & 3) == 0, "split-K scratch must be 16-byte aligned");
+        const int rc = launch_conv_tc_splitk(g, epi, passes, d->z, d->ZH, stream);
+        if (rc >= 0) return rc;
+    }
     if (d->impl == 4 && bn == 0 && conv_pair_supported(g)) return launch_conv_pair(g, epi, passes, stream);
     if (d->impl == 4) return launch_conv_tc(g, epi, bn, passes, stream);
     // per-layer choice of the product path (impl == 0), from per-layer timings of the three kernels on B200

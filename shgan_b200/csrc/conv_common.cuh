@@ -48,6 +48,9 @@ static inline ConvGeom make_geom(const shgan_conv_desc& d) {
 
 int launch_conv_simt(const ConvGeom& g, const EpiParams& epi, int block_n, cudaStream_t stream);
 int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream);
+// split-K for the 4x4 / 8x8 layers (conv_tc.cu): scratch = max_splits partial buffers of N*OH*OW*Co floats; returns -1 when the
+// layer is not worth splitting (the caller then takes the normal path)
+int launch_conv_tc_splitk(const ConvGeom& g, const EpiParams& epi, int passes, float* scratch, int max_splits, cudaStream_t stream);
 int launch_conv_halo(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream);
 int launch_conv_pair(const ConvGeom& g, const EpiParams& epi, int passes, cudaStream_t stream);
 bool conv_pair_supported(const ConvGeom& g);
@@ -152,8 +155,8 @@ __device__ __forceinline__ void epilogue_apply_staged(const EpiParams& p, const 
 
 // raw-mode store of CH consecutive channels of output pixel (n,y,x) into the strided z tensor
 template <int CH>
-__device__ __forceinline__ void raw_store(const ConvGeom& g, const float* v, int n, int y, int x, int o0) {
-    const long long zi = (((long long)n * g.ZH + (y * g.zsy + g.zoy)) * g.ZW + (x * g.zsx + g.zox)) * g.Co + o0;
+__device__ __forceinline__ void raw_store(const ConvGeom& g, const float* v, int n, int y, int x, int o0, long long z_off = 0) {
+    const long long zi = z_off + (((long long)n * g.ZH + (y * g.zsy + g.zoy)) * g.ZW + (x * g.zsx + g.zox)) * g.Co + o0;
 #pragma unroll
     for (int i = 0; i < CH; i += 4)
         *reinterpret_cast<float4*>(g.z + zi + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);

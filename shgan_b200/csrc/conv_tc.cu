@@ -45,6 +45,10 @@ struct TileInfo {
     int TW, TH, TN;
     int tiles_x, tiles_y, tiles_n, nblk;
     int total;
+    // split-K (RAW mode into per-split partial buffers, summed by conv_splitk_epilogue_kernel): ksplit CTAs share one output
+    // tile, each running kit_per of the (tap, slab) iterations; ksplit == 1: off
+    int ksplit, kit_per;
+    long long split_stride;     // floats between partial buffers
 };
 
 constexpr int TC_THREADS = 384;      // warpgroup 0: warp 0 TMA, warp 1 MMA (2 idle); warpgroups 1-2 (warps 4..11): epilogue
@@ -128,17 +132,20 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
             uint32_t phase = 0;
             const uint32_t tx_bytes = (passes == 3 ? 2u : 1u) * (uint32_t)(A_BYTES + Cfg::B_BYTES);
             for (int tile = blockIdx.x; tile < ti.total; tile += gridDim.x) {
-                int m = tile / ti.nblk;
-                const int nb = tile - m * ti.nblk;
+                const int sp = tile % ti.ksplit;
+                int m = (tile / ti.ksplit) / ti.nblk;
+                const int nb = (tile / ti.ksplit) - m * ti.nblk;
                 const int x0 = (m % ti.tiles_x) * ti.TW;
                 m /= ti.tiles_x;
                 const int y0 = (m % ti.tiles_y) * ti.TH;
                 const int n0 = (m / ti.tiles_y) * ti.TN;
-                for (int t = 0; t < g.ntaps; ++t) {
+                const int kit0 = sp * ti.kit_per, kit1 = kit0 + ti.kit_per < kiters ? kit0 + ti.kit_per : kiters;
+                for (int t = kit0 / kslabs; t * kslabs < kit1; ++t) {
                     const int s = g.tap_src[t];
                     const int cx = x0 + g.tap_dx[t], cy = y0 + g.tap_dy[t];
                     const int wrow = g.tap_w[t] * g.Co + nb * BN;
-                    for (int ks = 0; ks < kslabs; ++ks) {
+                    const int ks0 = t * kslabs < kit0 ? kit0 - t * kslabs : 0, ks1 = (t + 1) * kslabs > kit1 ? kit1 - t * kslabs : kslabs;
+                    for (int ks = ks0; ks < ks1; ++ks) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                         mbar_expect_tx(&full_bar[stage], tx_bytes);
@@ -164,8 +171,10 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < ti.total; tile += gridDim.x) {
-                for (int it0 = 0; it0 < kiters; it0 += chunk_iters) {
-                    const int n_it = kiters - it0 < chunk_iters ? kiters - it0 : chunk_iters;
+                const int kit0s = (tile % ti.ksplit) * ti.kit_per;
+                const int kloc = (kit0s + ti.kit_per < kiters ? kit0s + ti.kit_per : kiters) - kit0s;   // this CTA's share of the K loop
+                for (int it0 = 0; it0 < kloc; it0 += chunk_iters) {
+                    const int n_it = kloc - it0 < chunk_iters ? kloc - it0 : chunk_iters;
                     mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -203,12 +212,15 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
         const int tx_i = row & (ti.TW - 1);
         const int ty_i = (row >> ti.tw_log2) & (ti.TH - 1);
         const int tn_i = row >> (ti.tw_log2 + ti.th_log2);
-        const int nchunks = (kiters + chunk_iters - 1) / chunk_iters;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < ti.total; tile += gridDim.x) {
-            int m = tile / ti.nblk;
-            const int nb = tile - m * ti.nblk;
+            const int sp = tile % ti.ksplit;
+            const int kit0s = sp * ti.kit_per;
+            const int kloc = (kit0s + ti.kit_per < kiters ? kit0s + ti.kit_per : kiters) - kit0s;
+            const int nchunks = (kloc + chunk_iters - 1) / chunk_iters;
+            int m = (tile / ti.ksplit) / ti.nblk;
+            const int nb = (tile / ti.ksplit) - m * ti.nblk;
             const int x = (m % ti.tiles_x) * ti.TW + tx_i;
             m /= ti.tiles_x;
             const int y = (m % ti.tiles_y) * ti.TH + ty_i;
@@ -234,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
                 // weight of this chunk in the register-level sum: 1 (fmaf(v, 1, acc) == acc + v exactly), or the per-pixel
                 // blend weight of the chunk's tap (ConvGeom::chunk_scale)
                 // times the compensation of the truncating accumulate for this chunk's chain of MMAs (ConvGeom::acc_comp)
-                const int n_it = kiters - c * chunk_iters < chunk_iters ? kiters - c * chunk_iters : chunk_iters;
+                const int n_it = kloc - c * chunk_iters < chunk_iters ? kloc - c * chunk_iters : chunk_iters;
                 const float csc = ((g.chunk_scale && valid) ? __ldg(g.chunk_scale + (long long)c * g.OH * g.OW + (long long)y * g.OW + x) : 1.f) *
                                   (1.f + g.acc_comp * (float)(n_it * (passes == 3 ? 12 : 4)));
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -257,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps maps, const ConvGeom g, const E
                 for (int p = 0; p < HN / 16; ++p) {
                     const int oi = half * HN + p * 16;
                     const int o0 = nb * BN + oi;
-                    if (g.mode == 1) raw_store<16>(g, accv + p * 16, n, y, x, o0);
+                    if (g.mode == 1) raw_store<16>(g, accv + p * 16, n, y, x, o0, (long long)sp * ti.split_stride);
                     else if (staged) epilogue_apply_staged<BN, 16>(epi, stg, accv + p * 16, nz, g.Co, o0, oi, rgb, pix);
                     else epilogue_apply<16>(epi, accv + p * 16, n, y, x, g.OH, g.OW, g.Co, o0, rgb, pix);
                     if ((p & 1) && g.mode == 0 && epi.rgb_w) {   // one torgb partial per CONV_RGB_BLOCK = 32 channels
@@ -299,7 +311,7 @@ static int launch_bn(const ConvTmaps& maps, const ConvGeom& g, const EpiParams& 
         })) return e;
     const int grid = ti.total < num_sms ? ti.total : num_sms;
     // two-level accumulation: at most TC_MAX_CHUNK_ITERS (tap, slab) steps are chained inside one TMEM accumulator
-    const int kiters = g.ntaps * (g.C / TC_KC);
+    const int kiters = ti.ksplit > 1 ? ti.kit_per : g.ntaps * (g.C / TC_KC);
     const int nchunks = ceil_div(kiters, TC_MAX_CHUNK_ITERS);
     int chunk_iters = ceil_div(kiters, nchunks);
     if (g.chunk_scale) {      // one chunk per tap (taps are the outer loop of the K order)
@@ -311,7 +323,8 @@ static int launch_bn(const ConvTmaps& maps, const ConvGeom& g, const EpiParams& 
     return 0;
 }
 
-int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream) {
+static int launch_conv_tc_impl(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream, int ksplit,
+                               long long split_stride) {
     SHGAN_CHECK(g.C % TC_KC == 0, "C must be a multiple of 64 for the tensor-core path");
     SHGAN_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
     TileInfo ti;
@@ -342,7 +355,10 @@ int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int pas
     }
     SHGAN_CHECK(g.Co % block_n == 0, "Co must be a multiple of block_n");
     ti.nblk = g.Co / block_n;
-    const long long total = (long long)ti.tiles_x * ti.tiles_y * ti.tiles_n * ti.nblk;
+    ti.ksplit = ksplit;
+    ti.kit_per = ceil_div(g.ntaps * (g.C / TC_KC), ksplit);
+    ti.split_stride = split_stride;
+    const long long total = (long long)ti.tiles_x * ti.tiles_y * ti.tiles_n * ti.nblk * ksplit;
     SHGAN_CHECK(total <= INT32_MAX, "too many tiles");
     ti.total = (int)total;
 
@@ -364,6 +380,89 @@ int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int pas
     if (block_n == 64) return launch_bn<64>(maps, g, epi, ti, passes, stream);
     if (block_n == 128) return launch_bn<128>(maps, g, epi, ti, passes, stream);
     return launch_bn<256>(maps, g, epi, ti, passes, stream);
+}
+
+int launch_conv_tc(const ConvGeom& g, const EpiParams& epi, int block_n, int passes, cudaStream_t stream) {
+    return launch_conv_tc_impl(g, epi, block_n, passes, stream, 1, 0);
+}
+
+// ---- split-K for the 4x4 / 8x8 layers ---------------------------------------------------------------------------------------
+// Those layers have 2-8 pixel tiles: 16-64 CTAs each chaining all 72 (tap, slab) steps (864 MMAs at the single-thread issue rate,
+// 78 us measured for 3.6 / 14.5 GFLOP).  Here `ksplit` CTAs share an output tile, each runs a slice of the K loop and writes its
+// fp32 partial tile into its own buffer (RAW mode); one small kernel sums the partials and applies the fused epilogue.  The
+// summation order is fixed (split 0, 1, 2, ...): results are deterministic.
+// thread = (pixel, 8 channels): 2 independent 128-bit loads per split; the torgb partial of a 32-channel block is summed over
+// the 4 adjacent lanes that hold it
+__global__ void __launch_bounds__(256)
+conv_splitk_epilogue_kernel(const float* __restrict__ z, int ksplit, long long split_stride, const EpiParams epi, int N, int OH, int OW,
+                            int Co) {
+    const int cgs = Co / 8;
+    const long long total = (long long)N * OH * OW * cgs;
+    for (long long gid0 = blockIdx.x * (long long)blockDim.x; gid0 < total; gid0 += (long long)gridDim.x * blockDim.x) {
+        const long long gid = gid0 + threadIdx.x;
+        const bool live = gid < total;                       // (total is a multiple of 4: the shuffles below stay inside a 32-channel block)
+        const int cg = (int)((live ? gid : 0) % cgs);
+        const long long pix = (live ? gid : 0) / cgs;
+        const int x = (int)(pix % OW), y = (int)((pix / OW) % OH), n = (int)(pix / ((long long)OW * OH));
+        const int o0 = cg * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (live) {
+            const float4* src = reinterpret_cast<const float4*>(z + pix * Co + o0);
+            const long long st4 = split_stride / 4;
+#pragma unroll 6
+            for (int sp = 0; sp < ksplit; ++sp) {
+                const float4 a = __ldg(src + sp * st4), b = __ldg(src + sp * st4 + 1);
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+            }
+        }
+        float rgb[3] = {0.f, 0.f, 0.f};
+        if (live) epilogue_apply<8>(epi, v, n, y, x, OH, OW, Co, o0, rgb, pix);
+        if (epi.rgb_w) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                rgb[j] += __shfl_xor_sync(0xffffffffu, rgb[j], 1);
+                rgb[j] += __shfl_xor_sync(0xffffffffu, rgb[j], 2);
+            }
+            if (live && (cg & 3) == 0)
+                *reinterpret_cast<float4*>(epi.rgb_out + (pix * (Co / CONV_RGB_BLOCK) + cg / 4) * 4) = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+        }
+    }
+}
+
+int launch_conv_tc_splitk(const ConvGeom& g0, const EpiParams& epi, int passes, float* scratch, int max_splits, cudaStream_t stream) {
+    if (g0.C % TC_KC != 0 || g0.Co % 128 != 0 || g0.mode != 0 || g0.chunk_scale) return -1;
+    int dev = 0, num_sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    // tiles of the un-split launch at BN = 128 (the MMA issue rate of one thread is the same for N = 64 and N = 128).  Layers whose
+    // BN = 128 tiles already fill the SMs (16x16 at batch 16) are left alone: splitting them at BN = 256 measured 53 + 9 us
+    // against 55 us un-split (two-stage operand pipeline at that width).
+    const int TW = pow2_ceil(g0.OW) < 16 ? pow2_ceil(g0.OW) : 16;
+    const int th_max = TC_M / TW;
+    const int TH = pow2_ceil(g0.OH) < th_max ? pow2_ceil(g0.OH) : th_max;
+    const int TN = TC_M / (TW * TH);
+    const long long tiles = (long long)ceil_div(g0.OW, TW) * ceil_div(g0.OH, TH) * ceil_div(g0.N, TN) * (g0.Co / 128);
+    const int kiters = g0.ntaps * (g0.C / TC_KC);
+    const int bn = 128;
+    int ksplit = (int)(num_sms / tiles);
+    if (ksplit > max_splits) ksplit = max_splits;
+    if (ksplit > kiters / 2) ksplit = kiters / 2;          // at least two K steps per CTA
+    if (ksplit < 2) return -1;                             // enough tiles already: not worth a second launch
+    ksplit = ceil_div(kiters, ceil_div(kiters, ksplit));   // no empty split
+    ConvGeom g = g0;
+    g.mode = 1;
+    g.z = scratch;
+    g.ZH = g0.OH; g.ZW = g0.OW; g.zsy = 1; g.zsx = 1; g.zoy = 0; g.zox = 0;
+    const long long stride = (long long)g0.N * g0.OH * g0.OW * g0.Co;
+    if (int e = launch_conv_tc_impl(g, EpiParams{}, bn, passes, stream, ksplit, stride)) return e;
+    const long long items = (long long)g0.N * g0.OH * g0.OW * (g0.Co / 8);
+    long long blocks = ceil_div64(items, 256);
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    conv_splitk_epilogue_kernel<<<(unsigned)blocks, 256, 0, stream>>>(scratch, ksplit, stride, epi, g0.N, g0.OH, g0.OW, g0.Co);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // namespace shgan

@@ -269,8 +269,22 @@ class GeneratorEngine:
             x = self._dense(spec, x, self._f32(f'map{i}', n, spec[0].shape[0]))
         return x
 
+    SPLITK_MAX_PIXELS = 2048          # N*OH*OW up to here (4x4 / 8x8 at batch 16-32): too few tiles to fill 148 SMs
+    SPLITK_BYTES = 16 << 20
+
+    def _splitk_scratch(self, n, oh, ow):
+        """fp32 scratch for the K-split of the 4x4 / 8x8 convolutions (shgan_conv_igemm, ACT mode with z set); None elsewhere."""
+        if n * oh * ow > self.SPLITK_MAX_PIXELS:
+            return None
+        b = self._buf.get('splitk')
+        if b is None:
+            b = torch.empty(self.SPLITK_BYTES // 4, dtype=torch.float32, device=self.dev)
+            self._buf['splitk'] = b
+        return b
+
     def _conv(self, srcs, L, taps, oh, ow, epi=None, raw=None):
-        K.conv_igemm(srcs, L['w_hi'], L['w_lo'], taps, oh, ow, epi=epi, raw=raw, passes=self.passes, impl=self.impl)
+        sk = self._splitk_scratch(srcs[0].shape[0], oh, ow) if raw is None else None
+        K.conv_igemm(srcs, L['w_hi'], L['w_lo'], taps, oh, ow, epi=epi, raw=raw, passes=self.passes, impl=self.impl, splitk=sk)
 
     def _enc_epi(self, L, out):
         a = self.eact

@@ -188,9 +188,11 @@ def nhwc_to_nchw_f32(x):
 
 # ---- convolution -------------------------------------------------------------------------------------
 @_on_tensor_device
-def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0, acc_comp=None):
+def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0, acc_comp=None, splitk=None):
     """srcs: list of Planes [N,Hs,Ws,C]; w_hi/w_lo: fp16 [w_taps, Co, C]; taps: list of (src, dy, dx, w_tap).
-    epi: Epilogue (ACT mode)  or  raw = (z fp32 [N,ZH,ZW,Co], zsy, zsx, zoy, zox) (RAW mode)."""
+    epi: Epilogue (ACT mode)  or  raw = (z fp32 [N,ZH,ZW,Co], zsy, zsx, zoy, zox) (RAW mode).
+    splitk (ACT mode): an fp32 scratch tensor; layers with too few output tiles to fill the GPU (4x4, 8x8) are then split along K
+    over several CTAs per tile (the library decides; the scratch must hold at least two partial outputs)."""
     d = ConvDesc()
     d.num_src = len(srcs)
     n, _, _, c = srcs[0].shape
@@ -210,6 +212,11 @@ def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, pa
     else:
         d.mode = 0
         d.epi = epi
+        if splitk is not None:
+            per = n * oh * ow * d.Co
+            nbuf = min(int(splitk.numel() // per), 64)
+            if nbuf >= 2:
+                d.z = _p(splitk); d.ZH = nbuf; d.ZW = per
     d.block_n = block_n; d.passes = passes; d.impl = impl
     d.acc_comp = ACC_COMP if acc_comp is None else acc_comp    # 0 = library default, < 0 = off (include/shgan_b200.h)
     if impl == 1:       # fp32 FMA cross-check: lives in the test-only library, not in libshgan_b200.so

@@ -89,7 +89,7 @@ def conv_num_nblocks(co, block_n=0):
     return co // 32
 
 
-def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0, acc_comp=None):
+def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, passes=3, impl=0, acc_comp=None, splitk=None):
     n, _, _, c = srcs[0].shape
     w = w_hi.float() + w_lo.float()          # [T, Co, C]
     co = w.shape[1]

@@ -72,6 +72,39 @@ def test_igemm_plain(shape, impl):
     assert relerr(y, ref) <= 3e-6, relerr(y, ref)
 
 
+@pytest.mark.parametrize('shape', [(16, 512, 512, 4, 4), (16, 256, 512, 8, 8), (5, 128, 128, 4, 4), (3, 64, 256, 5, 7), (2, 64, 128, 24, 24)],
+                         ids=str)
+def test_igemm_split_k(shape):
+    """ACT mode with a split-K scratch (4x4 / 8x8 layers: several CTAs per output tile, fp32 partials, reduce + fused epilogue
+    kernel) against the fp64 convolution with bias + lrelu + fused torgb partial sums, and bit-identical across two runs
+    (fixed summation order).  The last shape has enough tiles: the library falls back to the un-split launch."""
+    from shgan_b200 import kernels as K, packing as P
+    n, ci, co, h, w = shape
+    g = np.random.default_rng(sum(shape))
+    x = g.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = (g.standard_normal((co, ci, 3, 3)) / np.sqrt(ci * 9)).astype(np.float32)
+    bias = g.standard_normal(co).astype(np.float32)
+    rgb_w = g.standard_normal((3, co)).astype(np.float32)
+    rgb_style = g.standard_normal((n, co)).astype(np.float32)
+    xp = K.nchw_to_planes(t(x))
+    wh, wl = P.pack_conv_weight(t(wt))
+    scratch = torch.empty(4 << 20, device=DEV)
+    outs = []
+    for _ in range(2):
+        y = torch.empty((n, h, w, co), device=DEV)
+        part = torch.zeros((n, h, w, co // 32, 4), device=DEV)
+        epi = K.make_epilogue(bias=t(bias), act=True, act_alpha=0.2, act_gain=float(np.sqrt(2)), act_clamp=256.0, out_f32=y,
+                              rgb_w=t(rgb_w), rgb_style=t(rgb_style), rgb_out=part)
+        K.conv_igemm([xp], wh, wl, P.taps_plain(3, 3), h, w, epi=epi, splitk=scratch)
+        outs.append((K.nhwc_to_nchw_f32(y).cpu().numpy(), part.cpu().numpy()))
+    ref = O.conv2d(x.astype(np.float64), wt.astype(np.float64), padding=1) + bias[None, :, None, None]
+    ref = np.where(ref >= 0, ref, 0.2 * ref) * np.sqrt(2)
+    assert relerr(outs[0][0], ref) <= 3e-6
+    rgb = np.einsum('nchw,jc,nc->njhw', ref, rgb_w.astype(np.float64), rgb_style.astype(np.float64))
+    assert relerr(outs[0][1][..., :3].sum(3).transpose(0, 3, 1, 2), rgb) <= 1e-5
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_igemm_tc_single_pass_and_block_n():
     g = np.random.default_rng(11)
     x = g.standard_normal((2, 64, 16, 16)).astype(np.float32)
