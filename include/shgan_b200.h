@@ -174,9 +174,11 @@ typedef struct {
     float fx[4], fy[4];
     float gain;
     shgan_epilogue epi;
-    int passes;                  /* 3 (default when 0) or 1, as in shgan_conv_desc */
+    int passes;                  /* 3 (default when 0) or 1, as in shgan_conv_desc; | SHGAN_UP2_NARROW forces the 8-warp
+                                    epilogue instance where the library would pick the 16-warp one (C <= 256): tests, profiling */
     float acc_comp;              /* as in shgan_conv_desc */
 } shgan_up2_desc;
+#define SHGAN_UP2_NARROW 0x100
 int shgan_conv_up2(const shgan_up2_desc* d, void* stream);
 
 /* ---- FIR (blur) on NHWC data with the fused pointwise epilogue ---------------------------

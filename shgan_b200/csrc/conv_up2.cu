@@ -54,9 +54,17 @@ struct Up2Params {
     int sg_units[4], sg_ubase[4];
 };
 
-constexpr int U2_THREADS = 384;
-constexpr int U2_EPI_THREADS = 256;
-constexpr int U2_REGS_DEC = 56, U2_REGS_INC = 224;
+// Two instances.  WIDE = false: 8 epilogue warps with the whole tile's accumulator sums in registers (any number of TMEM chunks per
+// tile).  WIDE = true (C <= 256: the tile is ONE chunk, so the accumulator can stay in TMEM until the z tile is free): 16 epilogue
+// warps, thread = tile position x ONE parity block for the drain and 4 channels x 1 output column x 6 output rows for the blur --
+// the 512^2 / 256^2 layers are bound by the epilogue's instruction issue (profiles/r2_up2_findings.md), and twice the warps at
+// half the instructions each halve it.  Register pool of a CTA = threads x the launch allocation (168 / 96):
+// 128 x 56 + 256 x 224 = 384 x 168;  128 x 56 + 512 x 104 <= 640 x 96.
+template <bool WIDE> struct U2Cfg {
+    static constexpr int EPI_THREADS = WIDE ? 512 : 256;
+    static constexpr int THREADS = 128 + EPI_THREADS;
+    static constexpr int REGS_DEC = 56, REGS_INC = WIDE ? 104 : 224;
+};
 constexpr int U2_KC = 64;
 constexpr int U2_P = 16;                         // tile pitch (input columns per flattened row)
 constexpr int U2_ROWS = 8;                       // input rows per tile: U2_ROWS * U2_P = 128 = UMMA M
@@ -88,7 +96,8 @@ __device__ __forceinline__ float4 f4_fma(float a, const float4& x, const float4&
 }
 __device__ __forceinline__ float4 f4_mul(float a, const float4& x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
 
-__global__ void __launch_bounds__(U2_THREADS, 1)
+template <bool WIDE>
+__global__ void __launch_bounds__(U2Cfg<WIDE>::THREADS, 1)
 conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ Up2Params P, const EpiParams epi) {
     extern __shared__ uint8_t smem_raw[];
     // aligned by pointer arithmetic on the __shared__ array (not an integer round trip), so that the compiler keeps the
@@ -108,6 +117,8 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
     volatile int* epi_progress = reinterpret_cast<volatile int*>(bars + 17);   // index of the tile the epilogue is working on
     float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + U2_BAR_BYTES);   // [3][64]
 
+    constexpr int U2_THREADS = U2Cfg<WIDE>::THREADS, U2_EPI_THREADS = U2Cfg<WIDE>::EPI_THREADS;
+    constexpr int U2_REGS_DEC = U2Cfg<WIDE>::REGS_DEC, U2_REGS_INC = U2Cfg<WIDE>::REGS_INC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kslabs = P.C / U2_KC;
     const int nplanes = P.passes == 3 ? 2 : 1;
@@ -266,6 +277,138 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(U2_REGS_INC));
+        if constexpr (WIDE) {
+        // ===================== epilogue, 16 warps (warps 4..19), one TMEM chunk per tile =====================
+        const int e = (int)threadIdx.x - (U2_THREADS - U2_EPI_THREADS);
+        const int q = warp & 3;                 // TMEM lane quarter
+        const int pb = (warp - 4) >> 2;         // parity block = 64 accumulator columns: (1,0) (0,0) (0,1) (1,1)
+        const int row = q * 32 + lane;          // tile position
+        const int r = row >> 4, c = row & 15;
+        const int py = (pb == 0 || pb == 3) ? 1 : 0, px = pb >> 1;
+        // chained MMAs per column of my block: taps {2,4,2,1} x 4 k-steps x passes x slabs
+        const float comp = 1.f + P.acc_comp * (float)((P.passes == 3 ? 12 : 4) * P.chunk_slabs) * (pb == 1 ? 4.f : (pb == 3 ? 1.f : 2.f));
+        float4* const zt4 = reinterpret_cast<float4*>(zt);
+        float4* const zw = zt4 + ((2 * r + py) * 32 + 2 * c + px) * U2_ZT_PITCH;
+        // blur role: thread = 4 channels (quad q4) of one output column ox and one half (6 rows) of the tile's 12 output rows;
+        // output (oy, ox) reads z rows oy+1 .. oy+4 and z columns ox+1 .. ox+4
+        const int q4 = e & 7, ox = (e >> 3) & 31, hr = e >> 8;
+        const bool blur_active = ox < U2_OWN_X;
+        const float4* const zrd = zt4 + ((6 * hr + 1) * 32 + ox + 1) * U2_ZT_PITCH + q4;
+        const float gain_e = epi.act_gain;
+        const float alpha_e = epi.act ? epi.act_alpha : 1.f;
+        const float clamp_e = (epi.act && epi.act_clamp > 0.f) ? epi.act_clamp : __int_as_float(0x7f800000);
+        const float nstr = epi.noise ? __ldg(epi.noise_strength) * gain_e : 0.f;
+        const bool has_skip = epi.skip_hi != nullptr, has_noise = epi.noise != nullptr, has_f32 = epi.out_f32 != nullptr,
+                   has_planes = epi.out_hi != nullptr;
+        const int row_elems = P.OW * P.Co;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x, ++tile_iter) {
+            int m = tile / P.nblk;
+            const int nb = tile - m * P.nblk;
+            const int kx = m % P.tiles_x;
+            m /= P.tiles_x;
+            const int ky = m % P.tiles_y;
+            const int n = m / P.tiles_y;
+            if (e == 0) *epi_progress = tile_iter;
+            const int y0 = U2_OWN_Y * ky + 6 * hr, x = U2_OWN_X * kx + ox;     // my first output row, my output column
+            const int rows_valid = P.OH - y0 < 6 ? P.OH - y0 : 6;              // (may be <= 0)
+            const bool col_valid = blur_active && x < P.OW && rows_valid > 0;
+
+            mbar_wait(&t_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + pb * 64);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                // the z tile / staging area is free again (previous round's or tile's readers are done)
+                asm volatile("bar.sync 1, %0;" ::"n"(U2_EPI_THREADS) : "memory");
+                if (g == 0 && e < 64) {
+                    const int o = nb * 64 + e;
+                    const long long no = (long long)n * P.Co + o;
+                    stg[e] = (epi.dcoef ? __ldg(epi.dcoef + no) : 1.f) * epi.wgain * gain_e;
+                    stg[64 + e] = epi.bias ? __ldg(epi.bias + o) * gain_e : 0.f;
+                    stg[128 + e] = epi.next_scale ? __ldg(epi.next_scale + no) : 1.f;
+                }
+                {
+                    float v[32];
+                    tmem_ld32(taddr + g * 32, v);
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq)
+                        zw[qq] = make_float4(v[4 * qq] * comp, v[4 * qq + 1] * comp, v[4 * qq + 2] * comp, v[4 * qq + 3] * comp);
+                }
+                if (g == 1) {               // the accumulator buffer is drained: the MMAs of the next-but-one tile may overwrite it
+                    tc_fence_before();
+                    mbar_arrive(&t_empty[acc]);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(U2_EPI_THREADS) : "memory");
+                if (!col_valid) continue;
+
+                const int lc = g * 32 + q4 * 4;                      // my 4 channels inside this block of 64
+                const float4 sd = *reinterpret_cast<const float4*>(stg + lc);
+                const float4 sb = *reinterpret_cast<const float4*>(stg + 64 + lc);
+                const float4 sn = *reinterpret_cast<const float4*>(stg + 128 + lc);
+                const int eo = ((n * P.OH + y0) * P.OW + x) * P.Co + nb * 64 + lc;      // (n, y0, x, first channel)
+                const float* p_nz = epi.noise + ((long long)n * epi.noise_sn + (long long)y0 * P.OW + x);
+                auto hrow = [&](const float4* zp) -> float4 {
+                    const float4 l0 = zp[0], l1 = zp[U2_ZT_PITCH], l2 = zp[2 * U2_ZT_PITCH], l3 = zp[3 * U2_ZT_PITCH];
+                    return f4_fma(P.fx[3], l3, f4_fma(P.fx[2], l2, f4_fma(P.fx[1], l1, f4_mul(P.fx[0], l0))));
+                };
+                // skip planes / noise of a row are requested two rows before the row that consumes them
+                uint2 sh[6], sl[6];
+                float sz[6];
+                auto fetch = [&](int j) {
+                    sh[j] = make_uint2(0u, 0u); sl[j] = make_uint2(0u, 0u); sz[j] = 0.f;
+                    if (j < rows_valid) {
+                        if (has_skip) {
+                            sh[j] = __ldg(reinterpret_cast<const uint2*>(epi.skip_hi + eo + j * row_elems));
+                            sl[j] = __ldg(reinterpret_cast<const uint2*>(epi.skip_lo + eo + j * row_elems));
+                        }
+                        if (has_noise) sz[j] = __ldg(p_nz + j * P.OW);
+                    }
+                };
+                fetch(0); fetch(1);
+                float4 h[4];
+                h[0] = hrow(zrd); h[1] = hrow(zrd + U2_ZT_ROW); h[2] = hrow(zrd + 2 * U2_ZT_ROW);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    if (j + 2 < 6) fetch(j + 2);
+                    h[(j + 3) & 3] = hrow(zrd + (j + 3) * U2_ZT_ROW);
+                    if (j < rows_valid) {
+                        const float4 o = f4_fma(P.fy[3], h[(j + 3) & 3], f4_fma(P.fy[2], h[(j + 2) & 3], f4_fma(P.fy[1], h[(j + 1) & 3], f4_mul(P.fy[0], h[j & 3]))));
+                        const float nzs = sz[j] * nstr;
+                        float v0 = fmaf(o.x, sd.x, nzs) + sb.x, v1 = fmaf(o.y, sd.y, nzs) + sb.y;
+                        float v2 = fmaf(o.z, sd.z, nzs) + sb.z, v3 = fmaf(o.w, sd.w, nzs) + sb.w;
+                        v0 = fminf(fmaxf(fmaxf(v0, v0 * alpha_e), -clamp_e), clamp_e);
+                        v1 = fminf(fmaxf(fmaxf(v1, v1 * alpha_e), -clamp_e), clamp_e);
+                        v2 = fminf(fmaxf(fmaxf(v2, v2 * alpha_e), -clamp_e), clamp_e);
+                        v3 = fminf(fmaxf(fmaxf(v3, v3 * alpha_e), -clamp_e), clamp_e);
+                        {
+                            const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&sh[j].x));
+                            const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&sh[j].y));
+                            const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&sl[j].x));
+                            const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&sl[j].y));
+                            v0 += a0.x + b0.x; v1 += a0.y + b0.y; v2 += a1.x + b1.x; v3 += a1.y + b1.y;
+                        }
+                        const int eoj = eo + j * row_elems;
+                        if (has_f32) *reinterpret_cast<float4*>(epi.out_f32 + eoj) = make_float4(v0, v1, v2, v3);
+                        if (has_planes) {
+                            v0 *= sn.x; v1 *= sn.y; v2 *= sn.z; v3 *= sn.w;
+                            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+                            *reinterpret_cast<uint2*>(epi.out_hi + eoj) =
+                                make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                            *reinterpret_cast<uint2*>(epi.out_lo + eoj) =
+                                make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+                        }
+                    }
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        } else {
         // ===================== epilogue (warps 4..11) =====================
         const int e = (int)threadIdx.x - (U2_THREADS - U2_EPI_THREADS);
         const int q = warp & 3;                 // TMEM lane quarter
@@ -434,6 +577,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                 }
             }
         }
+        }   // !WIDE
     }
 
     tc_fence_before();
@@ -456,7 +600,8 @@ extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
     SHGAN_CHECK(d->C >= 64 && d->C % 64 == 0 && d->Co >= 64 && d->Co % 64 == 0, "C and Co must be multiples of 64");
     SHGAN_CHECK((long long)d->N * d->C * d->H * d->W <= INT32_MAX, "input tensor is too large");
     SHGAN_CHECK(4LL * d->N * d->Co * d->H * d->W <= INT32_MAX, "output tensor is too large");
-    SHGAN_CHECK(d->passes == 0 || d->passes == 1 || d->passes == 3, "passes must be 0, 1 or 3");
+    const int passes_arg = d->passes & ~SHGAN_UP2_NARROW;
+    SHGAN_CHECK(passes_arg == 0 || passes_arg == 1 || passes_arg == 3, "passes must be 0, 1 or 3");
     if (const char* m = check_epi(d->epi, d->Co)) SHGAN_CHECK(false, m);
     SHGAN_CHECK(!d->epi.rgb_w, "the up-sampling convolution has no fused torgb");
     if (d->N == 0) return 0;
@@ -472,10 +617,13 @@ extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
     P.total = (int)total;
     for (int i = 0; i < 4; ++i) { P.fx[i] = d->fx[i]; P.fy[i] = d->fy[i] * d->gain; }
     P.acc_comp = d->acc_comp == 0.f ? SHGAN_ACC_COMP_DEFAULT : (d->acc_comp < 0.f ? 0.f : d->acc_comp);
-    P.passes = d->passes == 0 ? 3 : d->passes;
+    P.passes = passes_arg == 0 ? 3 : passes_arg;
     // C >= 256: four slabs (<= 192 chained MMAs per column, compensated by acc_comp) per TMEM chunk, so that the two
     // accumulator buffers let the MMAs run a whole 512-channel tile ahead of the epilogue warps
     P.chunk_slabs = (d->C / 64) % 4 == 0 ? 4 : ((d->C / 64) % 2 == 0 && d->C >= 256 ? 2 : 1);
+    // C <= 256: the whole tile is one chunk (<= 192 chained MMAs per column) and the 16-warp epilogue instance runs
+    const bool wide = d->C <= 256 && !(d->passes & SHGAN_UP2_NARROW);
+    if (wide) P.chunk_slabs = d->C / 64;
     for (int sg = 0; sg < 4; ++sg) {
         P.sg_idesc[sg] = (1u << 4) | ((uint32_t)(u2_n(sg) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         P.sg_col[sg] = (uint32_t)u2_col(sg);
@@ -498,12 +646,14 @@ extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
     static DeviceInit once;
     int num_sms = 0;
     if (int e = device_init(once, &num_sms, []() -> int {
-            SHGAN_CUDA(cudaFuncSetAttribute(conv_up2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
+            SHGAN_CUDA(cudaFuncSetAttribute(conv_up2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
+            SHGAN_CUDA(cudaFuncSetAttribute(conv_up2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
             return 0;
         })) return e;
     const int grid = P.total < num_sms ? P.total : num_sms;
     const EpiParams epi = make_epi(d->epi);
-    conv_up2_kernel<<<grid, U2_THREADS, U2_SMEM_BYTES, stream>>>(maps, P, epi);
+    if (wide) conv_up2_kernel<true><<<grid, U2Cfg<true>::THREADS, U2_SMEM_BYTES, stream>>>(maps, P, epi);
+    else conv_up2_kernel<false><<<grid, U2Cfg<false>::THREADS, U2_SMEM_BYTES, stream>>>(maps, P, epi);
     SHGAN_LAUNCH_CHECK();
     return 0;
 }

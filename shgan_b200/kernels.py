@@ -229,10 +229,14 @@ def conv_igemm(srcs, w_hi, w_lo, taps, oh, ow, epi=None, raw=None, block_n=0, pa
     _lib.check(lib.shgan_conv_igemm(C.byref(d), _stream()), 'shgan_conv_igemm')
 
 
+UP2_NARROW = 0x100      # SHGAN_UP2_NARROW
+
+
 @_on_tensor_device
-def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None):
+def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None, narrow=False):
     """Fused up-sampling convolution (shgan_conv_up2): src Planes [N,H,W,C]; w_hi/w_lo fp16 [Co/64, 9, 64, C] from
-    packing.pack_up2_weight; fx/fy: the separable blur taps as applied (4 floats each); epi: Epilogue at [N,2H,2W,Co]."""
+    packing.pack_up2_weight; fx/fy: the separable blur taps as applied (4 floats each); epi: Epilogue at [N,2H,2W,Co].
+    narrow=True forces the 8-warp epilogue instance (tests / profiling)."""
     d = Up2Desc()
     n, h, w, c = src.shape
     d.src_hi = _p(src.hi); d.src_lo = _p(src.lo)
@@ -242,7 +246,7 @@ def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None):
         d.fx[i] = float(fx[i]); d.fy[i] = float(fy[i])
     d.gain = float(gain)
     d.epi = epi
-    d.passes = passes
+    d.passes = passes | (UP2_NARROW if narrow else 0)
     d.acc_comp = ACC_COMP if acc_comp is None else acc_comp
     lib = _lib.load()
     _lib.check(lib.shgan_conv_up2(C.byref(d), _stream()), 'shgan_conv_up2')

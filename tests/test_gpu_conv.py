@@ -304,9 +304,13 @@ UP2_SHAPES = [(2, 64, 64, 8, 8), (1, 128, 64, 20, 23), (2, 64, 128, 13, 7), (1, 
 
 @pytest.mark.parametrize('shape', UP2_SHAPES, ids=[str(s) for s in UP2_SHAPES])
 @pytest.mark.parametrize('passes', [3, 1])
-def test_conv_up2_tc_vs_fp64(shape, passes):
+@pytest.mark.parametrize('narrow', [False, True], ids=['auto', 'narrow'])
+def test_conv_up2_tc_vs_fp64(shape, passes, narrow):
+    """Both epilogue instances of the fused kernel: C <= 256 runs the 16-warp one unless `narrow` forces the 8-warp one."""
     from shgan_b200 import kernels as K, packing as P
     n, ci, co, h, wd = shape
+    if narrow and ci > 256:
+        pytest.skip('C > 256 always runs the 8-warp epilogue')
     g = torch.Generator().manual_seed(ci * 7 + co + h)
     x = torch.randn(n, ci, h, wd, generator=g).to(DEV)
     w = (torch.randn(co, ci, 3, 3, generator=g) / (3 * ci ** 0.5)).to(DEV)
@@ -318,7 +322,7 @@ def test_conv_up2_tc_vs_fp64(shape, passes):
     uh, ul = P.pack_up2_weight(w)
     # raw accumulator path (identity epilogue)
     y32 = torch.empty((n, 2 * h, 2 * wd, co), device=DEV)
-    K.conv_up2(xp, uh, ul, fx, fy, 4.0 / 49.0, K.make_epilogue(out_f32=y32), passes=passes)
+    K.conv_up2(xp, uh, ul, fx, fy, 4.0 / 49.0, K.make_epilogue(out_f32=y32), passes=passes, narrow=narrow)
     tol = 1e-5 if passes == 3 else 5e-3
     assert relerr(y32.permute(0, 3, 1, 2).cpu().numpy(), ref.cpu().numpy()) <= tol
     # full epilogue: demod, per-sample noise, bias, lrelu + clamp, skip, next-layer style; planes + fp32 outputs
@@ -332,7 +336,7 @@ def test_conv_up2_tc_vs_fp64(shape, passes):
     K.conv_up2(xp, uh, ul, fx, fy, 4.0 / 49.0,
                K.make_epilogue(dcoef=dc, wgain=0.7, noise=nzv, noise_sn=4 * h * wd, noise_strength=strength, bias=bias, act=True,
                                act_alpha=0.2, act_gain=2 ** 0.5, act_clamp=3.0, skip=K.nchw_to_planes(skip), next_scale=ns, out=out,
-                               out_f32=y32), passes=passes)
+                               out_f32=y32), passes=passes, narrow=narrow)
     v = ref * dc[:, :, None, None] * 0.7 + nzv * 0.3 + bias[None, :, None, None]
     v = (torch.where(v >= 0, v, v * 0.2) * 2 ** 0.5).clamp(-3.0, 3.0)
     sk = K.planes_to_nchw(K.nchw_to_planes(skip)).double()
