@@ -14,46 +14,89 @@ namespace shgan {
 
 constexpr int DCH = 512;  // input features per staged chunk: 4 x 128-bit weight loads in flight per lane
 
+// barrier over all threads of the thread-block cluster (release / acquire: shared-memory writes before it are visible to
+// distributed-shared-memory reads after it)
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// reads a float at the same shared-memory offset as `p` in the block of rank `rank` of this cluster
+__device__ __forceinline__ float ld_dsmem_f32(const float* p, int rank) {
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-// Block = 8 warps = 8 output features; the NB input rows of the current chunk are staged once per block in shared
-// memory (coalesced), each warp streams its own weight-row chunk from HBM with 4 independent 128-bit loads per lane.
+// Block = 8 warps x 2 output features each over ONE slice of the input features; the KS blocks of a thread-block cluster
+// share the same 16 outputs and split I between them.  The NB input rows of the current 512-feature chunk are staged
+// once per block in shared memory (coalesced); each lane keeps 2 rows x 4 x 128-bit weight loads in flight and requests
+// the NEXT chunk's weights before it consumes the current one, so a block always has 32 KB of HBM requests outstanding
+// (measured before: one row per warp, loads issued only after the previous chunk's FMAs, <= 148 blocks for the
+// 8192 -> 1024 layer: 0.4 TB/s).  Two rows per warp halve the shared-memory reads per weight byte (the x fragment is
+// reused from registers).  The cluster's partial sums are reduced in a fixed order by its first block through
+// distributed shared memory: deterministic, no workspace, one launch.
+constexpr int DROWS = 16;     // output features per block
+
 template <int NB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dense_kernel(const float* __restrict__ x0, long long x0_stride, int I0, const float* __restrict__ x1, long long x1_stride,
              const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y, long long y_stride, int B,
-             int I, int O, float wgain, float bgain, int act, float act_alpha, float act_gain, float act_clamp) {
+             int I, int O, float wgain, float bgain, int act, float act_alpha, float act_gain, float act_clamp, int kslice, int KS) {
     __shared__ __align__(16) float xs[NB][DCH];
+    __shared__ float part[DROWS][NB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o = blockIdx.x * 8 + warp;
-    const bool live = o < O;
-    const float* wr = w + (long long)(live ? o : 0) * I;
+    const int o = blockIdx.y * DROWS + warp * 2;
+    const bool live0 = o < O, live1 = o + 1 < O;
+    const int kbeg = blockIdx.x * kslice, kend = min(I, kbeg + kslice);      // gridDim.x == KS == the cluster size
+    const float* wr0 = w + (long long)(live0 ? o : 0) * I;
+    const float* wr1 = w + (long long)(live1 ? o + 1 : 0) * I;
+    auto load_w = [&](int ic, float4 (&a)[DCH / 128], float4 (&b)[DCH / 128]) {
+#pragma unroll
+        for (int u = 0; u < DCH / 128; ++u) {
+            const int i = ic + u * 128 + lane * 4;
+            const bool in = i < kend;
+            a[u] = (live0 && in) ? __ldg(reinterpret_cast<const float4*>(wr0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            b[u] = (live1 && in) ? __ldg(reinterpret_cast<const float4*>(wr1 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
     for (int b0 = 0; b0 < B; b0 += NB) {
-        float acc[NB];
+        float acc0[NB], acc1[NB];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) acc[j] = 0.f;
-        for (int ic = 0; ic < I; ic += DCH) {
-            float4 wv[DCH / 128];
-#pragma unroll
-            for (int u = 0; u < DCH / 128; ++u) {
-                const int i = ic + u * 128 + lane * 4;
-                wv[u] = (live && i < I) ? __ldg(reinterpret_cast<const float4*>(wr + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int j = 0; j < NB; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+        float4 wa[DCH / 128], wb[DCH / 128], na[DCH / 128], nb[DCH / 128];
+        if (kbeg < kend) load_w(kbeg, wa, wb);
+        for (int ic = kbeg; ic < kend; ic += DCH) {
+            if (ic + DCH < kend) load_w(ic + DCH, na, nb);
             __syncthreads();   // previous chunk fully consumed
-            for (int q = threadIdx.x; q < NB * (DCH / 4); q += 256) {
-                const int j = q / (DCH / 4), i = ic + (q % (DCH / 4)) * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b0 + j < B && i < I) {
-                    // I0 is a multiple of 4, so a quad never straddles the two concatenated inputs
-                    const float* xp = i < I0 ? x0 + (long long)(b0 + j) * x0_stride + i
-                                             : x1 + (long long)(b0 + j) * x1_stride + (i - I0);
-                    v = __ldg(reinterpret_cast<const float4*>(xp));
+            {
+                // all of a thread's input quads are requested before the first one is stored (one L2 round trip per chunk,
+                // not NB / 2 dependent ones)
+                constexpr int XQ = NB * (DCH / 4) / 256;
+                float4 xv[XQ];
+#pragma unroll
+                for (int t = 0; t < XQ; ++t) {
+                    const int q = threadIdx.x + t * 256;
+                    const int j = q / (DCH / 4), i = ic + (q % (DCH / 4)) * 4;
+                    xv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0 + j < B && i < kend) {
+                        // I0 is a multiple of 4, so a quad never straddles the two concatenated inputs
+                        const float* xp = i < I0 ? x0 + (long long)(b0 + j) * x0_stride + i
+                                                 : x1 + (long long)(b0 + j) * x1_stride + (i - I0);
+                        xv[t] = __ldg(reinterpret_cast<const float4*>(xp));
+                    }
                 }
-                *reinterpret_cast<float4*>(&xs[j][(q % (DCH / 4)) * 4]) = v;
+#pragma unroll
+                for (int t = 0; t < XQ; ++t) {
+                    const int q = threadIdx.x + t * 256;
+                    *reinterpret_cast<float4*>(&xs[q / (DCH / 4)][(q % (DCH / 4)) * 4]) = xv[t];
+                }
             }
             __syncthreads();
 #pragma unroll
@@ -61,26 +104,34 @@ dense_kernel(const float* __restrict__ x0, long long x0_stride, int I0, const fl
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
                     const float4 xv = *reinterpret_cast<const float4*>(&xs[j][u * 128 + lane * 4]);
-                    acc[j] = fmaf(xv.x, wv[u].x, acc[j]);
-                    acc[j] = fmaf(xv.y, wv[u].y, acc[j]);
-                    acc[j] = fmaf(xv.z, wv[u].z, acc[j]);
-                    acc[j] = fmaf(xv.w, wv[u].w, acc[j]);
+                    acc0[j] = fmaf(xv.x, wa[u].x, acc0[j]); acc1[j] = fmaf(xv.x, wb[u].x, acc1[j]);
+                    acc0[j] = fmaf(xv.y, wa[u].y, acc0[j]); acc1[j] = fmaf(xv.y, wb[u].y, acc1[j]);
+                    acc0[j] = fmaf(xv.z, wa[u].z, acc0[j]); acc1[j] = fmaf(xv.z, wb[u].z, acc1[j]);
+                    acc0[j] = fmaf(xv.w, wa[u].w, acc0[j]); acc1[j] = fmaf(xv.w, wb[u].w, acc1[j]);
                 }
             }
+#pragma unroll
+            for (int u = 0; u < DCH / 128; ++u) { wa[u] = na[u]; wb[u] = nb[u]; }
         }
 #pragma unroll
-        for (int j = 0; j < NB; ++j) acc[j] = warp_sum(acc[j]);
-        if (lane == 0 && live) {
-            const float bv = bias ? __ldg(bias + o) * bgain : 0.f;
+        for (int j = 0; j < NB; ++j) { acc0[j] = warp_sum(acc0[j]); acc1[j] = warp_sum(acc1[j]); }
+        __syncthreads();        // (the previous batch group's partials have been read)
+        if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                if (b0 + j < B) {
-                    float v = acc[j] * wgain + bv;
-                    if (act) v = lrelu_agc(v, act_alpha, act_gain, act_clamp);
-                    y[(long long)(b0 + j) * y_stride + o] = v;
-                }
+            for (int j = 0; j < NB; ++j) { part[warp * 2][j] = acc0[j]; part[warp * 2 + 1][j] = acc1[j]; }
+        }
+        if (KS > 1) cluster_sync_all(); else __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x < DROWS * NB) {
+            const int rr = threadIdx.x / NB, j = threadIdx.x % NB, oo = blockIdx.y * DROWS + rr;
+            float v = part[rr][j];
+            for (int r = 1; r < KS; ++r) v += ld_dsmem_f32(&part[rr][j], r);      // fixed order: deterministic
+            if (oo < O && b0 + j < B) {
+                v = v * wgain + (bias ? __ldg(bias + oo) * bgain : 0.f);
+                if (act) v = lrelu_agc(v, act_alpha, act_gain, act_clamp);
+                y[(long long)(b0 + j) * y_stride + oo] = v;
             }
         }
+        if (KS > 1) cluster_sync_all();     // the peers' partials stay alive until the first block has read them
     }
 }
 
@@ -228,12 +279,31 @@ extern "C" int shgan_dense_fwd(const float* x0, int64_t x0_stride, int I0, const
     SHGAN_CHECK(I % 4 == 0 && I0 % 4 == 0 && x0_stride % 4 == 0 && x1_stride % 4 == 0, "feature counts/strides must be multiples of 4");
     SHGAN_CHECK(I0 >= 0 && I0 <= I && (I0 == I || x1), "second input missing");
     if (B == 0) return 0;
+    // split I over a cluster of KS blocks until the grid fills the GPU twice over (slices stay multiples of 128 features:
+    // one 128-bit weight load per lane)
+    const int row_blocks = ceil_div(O, DROWS);
+    int KS = 1;
+    while (KS < 8 && row_blocks * KS < 2 * 148 && I % (KS * 2 * 128) == 0 && I / (KS * 2) >= 128) KS *= 2;
+    const int kslice = I / KS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)KS, (unsigned)row_blocks, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)KS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = KS > 1 ? 1 : 0;
+    const long long x0s = x0_stride, x1s = x1_stride, ys = y_stride;
     if (B <= 8)
-        dense_kernel<8><<<ceil_div(O, 8), 256, 0, (cudaStream_t)stream>>>(x0, x0_stride, I0, x1, x1_stride, w, bias, y, y_stride,
-                                                                          B, I, O, wgain, bgain, act, act_alpha, act_gain, act_clamp);
+        SHGAN_CUDA(cudaLaunchKernelEx(&cfg, dense_kernel<8>, x0, x0s, I0, x1, x1s, w, bias, y, ys, B, I, O, wgain, bgain, act, act_alpha,
+                                      act_gain, act_clamp, kslice, KS));
     else
-        dense_kernel<16><<<ceil_div(O, 8), 256, 0, (cudaStream_t)stream>>>(x0, x0_stride, I0, x1, x1_stride, w, bias, y, y_stride,
-                                                                           B, I, O, wgain, bgain, act, act_alpha, act_gain, act_clamp);
+        SHGAN_CUDA(cudaLaunchKernelEx(&cfg, dense_kernel<16>, x0, x0s, I0, x1, x1s, w, bias, y, ys, B, I, O, wgain, bgain, act, act_alpha,
+                                      act_gain, act_clamp, kslice, KS));
     SHGAN_LAUNCH_CHECK();
     return 0;
 }

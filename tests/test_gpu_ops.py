@@ -119,6 +119,29 @@ def test_dense_mapping_golden(golden):
     assert relerr(o.cpu().numpy(), ref) <= 2e-6
 
 
+@pytest.mark.parametrize('shape', [(16, 8192, 1024, 8192), (19, 1024, 100, 1024), (3, 512, 512, 512), (16, 1536, 64, 512), (8, 2048, 40, 1024),
+                                   (33, 768, 17, 768)], ids=str)
+def test_dense_cluster_split(shape):
+    """Layers whose output count does not fill the GPU split the input features over a thread-block cluster (partial sums reduced
+    through distributed shared memory in a fixed order): against an fp64 matmul, twice (bit-identical: deterministic)."""
+    from shgan_b200 import kernels as K
+    b, i, o, i0 = shape
+    g = torch.Generator().manual_seed(b * 31 + o)
+    x0 = torch.randn(b, i0, generator=g).to(DEV)
+    x1 = torch.randn(b, i - i0, generator=g).to(DEV) if i > i0 else None
+    w = torch.randn(o, i, generator=g).to(DEV)
+    bias = torch.randn(o, generator=g).to(DEV)
+    y = torch.empty((b, o), device=DEV)
+    K.dense(x0, w, bias, y, 1.0 / np.sqrt(i), 0.7, True, 0.2, np.sqrt(2), 256.0, x1=x1)
+    xx = torch.cat([x0, x1], 1) if x1 is not None else x0
+    ref = xx.double() @ w.double().T / np.sqrt(i) + bias.double() * 0.7
+    ref = torch.where(ref >= 0, ref, ref * 0.2) * np.sqrt(2)
+    assert relerr(y.cpu().numpy(), ref.cpu().numpy()) <= 3e-6
+    y2 = torch.empty_like(y)
+    K.dense(x0, w, bias, y2, 1.0 / np.sqrt(i), 0.7, True, 0.2, np.sqrt(2), 256.0, x1=x1)
+    assert torch.equal(y, y2)
+
+
 def test_style_prep():
     from shgan_b200 import kernels as K
     r = np.random.default_rng(4)

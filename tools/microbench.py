@@ -20,7 +20,7 @@ dev = 'cuda'
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 which = sys.argv[1:] or ['dense', 'fir', 'fromrgb']
 if 'dense' in which:
-    for (B, I, O, I0) in [(16, 512, 512, 512), (16, 1536, 512, 512), (16, 1536, 64, 512), (16, 8192, 1024, 8192), (16, 1024, 8192, 1024), (4, 1536, 512, 512)]:
+    for (B, I, O, I0) in [(16, 512, 512, 512), (16, 1536, 512, 512), (16, 1536, 64, 512), (16, 8192, 1024, 8192), (16, 1024, 8192, 1024), (16, 1024, 8960, 512), (4, 1536, 512, 512)]:
         x0 = torch.randn(B, I0, device=dev); x1 = torch.randn(B, max(I - I0, 4), device=dev) if I > I0 else None
         w = torch.randn(O, I, device=dev); b = torch.randn(O, device=dev); out = torch.empty(B, O, device=dev)
         us = timeit(lambda: K.dense(x0, w, b, out, 0.1, 1.0, True, x1=x1), flush=flush)
