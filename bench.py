@@ -24,6 +24,9 @@ Weak scaling: every rank runs its own batch, the forward needs no collective.  R
                  the HBM-bound kernels: the stand-alone blur passes of the step; the SHU at the model's size measured HBM-sized
                  (config C5's input_res-64 point, batch 512, L2 flushed; the L2-resident in-step call rides along as `in_step`):
                  algorithmic GB/s against the measured HBM copy peak
+  roofline_upfirdn2d
+                 the op-level `shgan_upfirdn2d_fwd` (1:1 with the reference plugin's entry point) on the model's blur / up / down
+                 variants: algorithmic GB/s against the HBM peak, the reference's CUDA plugin timed beside it (N = 1 only)
   collective     (N > 1) the all-gather of [items, 2*2048+1] float64 detector features: bytes, ms, GB/s, order checked
   reference_gpu  the UNMODIFIED reference generator (baseline/_ref: cuDNN fp32, TF32 off, its own upfirdn2d CUDA plugin)
                  timed with the same CUDA events on the same GPU, same batch -- the same-box GPU speed-up column
@@ -254,6 +257,65 @@ def shu_sweep(dev, peaks, resolutions=(4, 8, 16, 32, 64, 128, 256, 512), iters=7
     del flush
     torch.cuda.empty_cache()
     return rows
+
+
+# ------------------------------------------------------------------------------------------------ upfirdn2d (the plugin's op)
+def upfirdn2d_roofline(dev, peaks, iters=7):
+    """`shgan_upfirdn2d_fwd` (the C-ABI entry point that replaces the reference's only native code, upfirdn2d.cpp:16 /
+    upfirdn2d.cu:29-200) through `ops.upfirdn2d`, on the variants the model runs at its largest resolution, batch 16:
+    algorithmic in + out bytes / CUDA-event time against the HBM peak, L2 flushed between iterations; the reference's own CUDA
+    plugin is timed on the same tensors when baseline/_ref is present."""
+    import numpy as np
+    import torch
+    from shgan_b200 import ops
+    from golden import ref_import
+    R = None
+    if ref_import.reference_available():
+        try:
+            R = ref_import.import_reference()
+            if not R.upfirdn2d._init():
+                R = None
+        except Exception:
+            R = None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    fo = ops.setup_filter([1, 3, 3, 1], device=torch.device(dev))
+    fr = R.upfirdn2d.setup_filter([1, 3, 3, 1], device=torch.device(dev)) if R is not None else None
+
+    def med(fn):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); e.synchronize()
+            ts.append(s.elapsed_time(e))
+        return float(np.median(ts))
+    cases = [('blur before the stride-2 conv (conv2d_resample.py:117-120): pad 2', (16, 64, 512, 512), dict(padding=[2, 2, 2, 2])),
+             ('blur after the transposed conv (conv2d_resample.py:139): pad 1, gain 4', (16, 64, 513, 513), dict(padding=[1, 1, 1, 1], gain=4)),
+             ('upsample2d of the image (comodgan.py:331-338): up 2', (16, 3, 256, 256), dict(up=2, padding=[2, 1, 2, 1], gain=4)),
+             ('downsample2d (stylegan.py:658-684 skip path): down 2', (16, 64, 512, 512), dict(down=2, padding=[1, 1, 1, 1]))]
+    rows = []
+    for what, shape, kw in cases:
+        x = torch.randn(shape, device=dev)
+        y = ops.upfirdn2d(x, fo, **kw)
+        byts = 4.0 * (x.numel() + y.numel())
+        ms = med(lambda: ops.upfirdn2d(x, fo, **kw))
+        row = dict(case=what, shape=list(shape), ms=ms, algorithmic_mb=byts / 1e6, gbs=byts / ms / 1e6, frac_of_hbm=byts / ms / 1e6 / peaks['hbm'])
+        if R is not None:
+            with torch.no_grad():
+                ms_r = med(lambda: R.upfirdn2d.upfirdn2d(x, fr, impl='cuda', **kw))
+            row['reference_plugin_ms'] = ms_r
+            row['reference_plugin_gbs'] = byts / ms_r / 1e6
+        rows.append(row)
+        del x, y
+    del flush
+    torch.cuda.empty_cache()
+    best = rows[0]
+    return dict(bound='hbm', kernel='shgan_upfirdn2d_fwd: upfirdn2d_tile_kernel (stride-1 blurs) / upfirdn2d_gather_kernel (up / down variants), NCHW fp32',
+                achieved=best['gbs'], peak=peaks['hbm'], unit='GB/s', frac=best['frac_of_hbm'], traffic=None,
+                peak_source=f'{peaks["src"]} HBM copy', l2_policy='256 MB buffer written between timed iterations',
+                note='headline = the pad-2 blur of a [16,64,512,512] tensor; every case of the model in `cases`', cases=rows)
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -664,6 +726,10 @@ def main():
                     rg['speedup_device_resident'] = value / rg['value']
                 line['reference_gpu'] = rg
             if not args.no_other_configs and args.config == 'c3':
+                try:
+                    line['roofline_upfirdn2d'] = upfirdn2d_roofline(dev, peaks)
+                except Exception as ex:
+                    line['roofline_upfirdn2d'] = dict(unavailable=f'{type(ex).__name__}: {str(ex)[:200]}')
                 line['other_configs'] = other_configs(dev, peaks)
             if not args.no_cpu_baseline and D is None:
                 cb, _, _ = reference_cpu_run(cfg, 2, 1, budget_s=25.0)

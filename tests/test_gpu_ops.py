@@ -60,6 +60,26 @@ def test_upfirdn2d_wrappers_and_sizes():
             assert np.abs(y - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), (fn.__name__, shape)
 
 
+@pytest.mark.parametrize('kind', ['rank1_asym', 'full_rank'])
+@pytest.mark.parametrize('flip', [False, True])
+def test_upfirdn2d_4x4_stride1_kernels(kind, flip):
+    """up == down == 1 with a 4x4 filter: outer products run the row-walking separable kernel, anything else the tile kernel
+    (the choice is made on the device); several column blocks / row segments, ragged widths (scalar-store path), crops."""
+    from shgan_b200 import ops
+    g = np.random.default_rng(7)
+    if kind == 'rank1_asym':
+        f = np.outer([1.0, 2.0, 3.0, 4.0], [4.0, -1.0, 2.0, 0.5]).astype(np.float32) / 20
+    else:
+        f = g.standard_normal((4, 4)).astype(np.float32)
+    for shape, pad in [((2, 3, 70, 130), [2, 2, 2, 2]), ((1, 2, 150, 257), [1, 1, 1, 1]), ((1, 1, 66, 300), [-1, 3, 0, -2]),
+                       ((3, 1, 5, 9), [3, 3, 3, 3]), ((1, 2, 131, 512), [2, 1, 1, 2])]:
+        x = g.standard_normal(shape).astype(np.float32)
+        y = ops.upfirdn2d(t(x), t(f), padding=pad, flip_filter=flip, gain=1.5).cpu().numpy()
+        ref = O.upfirdn2d(x, f, padding=pad, flip_filter=flip, gain=1.5)
+        assert y.shape == ref.shape
+        assert np.abs(y - ref).max() <= 3e-6 * max(1.0, np.abs(ref).max()), (kind, flip, shape, pad)
+
+
 def test_upfirdn2d_errors():
     from shgan_b200 import ops
     f = t(O.setup_filter([1, 3, 3, 1]))

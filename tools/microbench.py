@@ -18,7 +18,7 @@ def timeit(fn, iters=10, flush=None):
 
 dev = 'cuda'
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-which = sys.argv[1:] or ['dense', 'fir', 'fromrgb']
+which = sys.argv[1:] or ['dense', 'fir', 'fromrgb', 'upfirdn']
 if 'dense' in which:
     for (B, I, O, I0) in [(16, 512, 512, 512), (16, 1536, 512, 512), (16, 1536, 64, 512), (16, 8192, 1024, 8192), (16, 1024, 8192, 1024), (16, 1024, 8960, 512), (4, 1536, 512, 512)]:
         x0 = torch.randn(B, I0, device=dev); x1 = torch.randn(B, max(I - I0, 4), device=dev) if I > I0 else None
@@ -49,3 +49,12 @@ if 'fromrgb' in which:
     out = K.Planes.empty(16, 512, 512, 64, dev)
     us = timeit(lambda: K.fromrgb(x, w, b, 0.5, 0.2, 1.414, 256.0, out), flush=flush)
     print(f'fromrgb 16x512x512 4->64: {us:8.1f} us  {(x.numel()*4 + out.hi.numel()*4)/us/1e3:.0f} GB/s')
+if 'upfirdn' in which:
+    from shgan_b200 import ops
+    f = ops.setup_filter([1, 3, 3, 1], device=torch.device(dev))
+    for shape, kw in [((16, 64, 512, 512), dict(padding=[2, 2, 2, 2])), ((16, 64, 513, 513), dict(padding=[1, 1, 1, 1], gain=4)),
+                      ((16, 3, 256, 256), dict(up=2, padding=[2, 1, 2, 1], gain=4)), ((16, 64, 512, 512), dict(down=2, padding=[1, 1, 1, 1]))]:
+        x = torch.randn(shape, device=dev)
+        y = ops.upfirdn2d(x, f, **kw)
+        us = timeit(lambda: ops.upfirdn2d(x, f, **kw), flush=flush)
+        print(f'upfirdn2d {shape} {kw}: {us:8.1f} us  {(x.numel() + y.numel()) * 4 / us / 1e3:.0f} GB/s')
