@@ -179,6 +179,8 @@ typedef struct {
     float acc_comp;              /* as in shgan_conv_desc */
 } shgan_up2_desc;
 #define SHGAN_UP2_NARROW 0x100
+#define SHGAN_UP2_CLUSTER 0x200     /* | into passes: run as two-CTA clusters that share each weight load by TMA multicast (measured: no */
+#define SHGAN_UP2_NO_CLUSTER 0x400  /* faster than single CTAs, so off by default; kept selectable and tested) / forbid them */
 int shgan_conv_up2(const shgan_up2_desc* d, void* stream);
 
 /* ---- FIR (blur) on NHWC data with the fused pointwise epilogue ---------------------------

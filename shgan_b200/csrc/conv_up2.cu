@@ -42,6 +42,9 @@ struct Up2Params {
     int N, H, W, C, Co;          // input planes [N,H,W,C]; output [N,2H,2W,Co]
     int OH, OW;
     int tiles_x, tiles_y, nblk, total;
+    int cluster;                 // 1: launched as clusters of two CTAs that run the same channel block in lock step and share every
+                                 // weight load (each loads half of the units and multicasts them to both)
+    int total_m;                 // spatial tiles (tiles_x * tiles_y * N)
     float fx[4], fy[4];          // separable blur taps as applied (correlation order); gain folded into fy
     float acc_comp;
     int passes;
@@ -91,6 +94,57 @@ __host__ __device__ constexpr int u2_aoff(int sg) { return sg == 0 ? U2_P + 1 : 
 __host__ __device__ constexpr int u2_units(int sg) { return sg == 0 ? 4 : (sg == 3 ? 1 : 2); }
 __host__ __device__ constexpr int u2_ubase(int sg) { return sg == 0 ? 0 : (sg == 1 ? 4 : (sg == 2 ? 6 : 8)); }
 
+__device__ __forceinline__ uint32_t u2_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void u2_cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the box lands at the same shared-memory offset in BOTH CTAs of the pair and its bytes are credited to the barrier at the same
+// offset in both
+__device__ __forceinline__ void u2_tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"((uint16_t)3)
+        : "memory");
+}
+// arrives on the barrier at the same offset in BOTH CTAs once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void u2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+// Work distribution.  Without clusters a CTA walks tiles t = blockIdx.x, + gridDim.x, ... with t = m * nblk + nb.  With
+// clusters the PAIR walks virtual tiles v = (m-pair) * nblk + nb and CTA `rank` takes spatial tile m = 2 * (m-pair) + rank, so
+// both CTAs need the same weights at the same time; an odd last spatial tile leaves one CTA with an invalid tile that it still
+// runs (zero operands, nothing stored) to keep the weight pipeline in lock step.
+struct U2Walk {
+    int first, step, total, rank, cluster;
+};
+__device__ __forceinline__ U2Walk u2_walk(const Up2Params& P) {
+    U2Walk w;
+    w.cluster = P.cluster;
+    w.rank = P.cluster ? (int)u2_cluster_ctarank() : 0;
+    w.first = P.cluster ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    w.step = P.cluster ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    w.total = P.total;
+    return w;
+}
+__device__ __forceinline__ bool u2_decode(const Up2Params& P, const U2Walk& w, int v, int& nb, int& kx, int& ky, int& n) {
+    int m = v / P.nblk;
+    nb = v - m * P.nblk;
+    if (w.cluster) m = 2 * m + w.rank;
+    const bool valid = m < P.total_m;
+    kx = m % P.tiles_x;
+    m /= P.tiles_x;
+    ky = m % P.tiles_y;
+    n = m / P.tiles_y;
+    return valid;
+}
+
 __device__ __forceinline__ float4 f4_fma(float a, const float4& x, const float4& acc) {
     return make_float4(fmaf(a, x.x, acc.x), fmaf(a, x.y, acc.y), fmaf(a, x.z, acc.z), fmaf(a, x.w, acc.w));
 }
@@ -134,7 +188,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
         }
         for (int s = 0; s < 4; ++s) {
             mbar_init(&w_full[s], 1);
-            mbar_init(&w_empty[s], 1);
+            mbar_init(&w_empty[s], P.cluster ? 2 : 1);      // a weight region is free when BOTH CTAs' MMAs have read it
         }
         mbar_fence_init();
     }
@@ -144,8 +198,10 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
     }
     tc_fence_before();
     __syncthreads();
+    if (P.cluster) u2_cluster_sync_all();        // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const U2Walk walk = u2_walk(P);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(U2_REGS_DEC));
@@ -155,12 +211,9 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                 int buf = 0;
                 uint32_t phase = 0;
                 const uint32_t tx_bytes = (uint32_t)nplanes * (uint32_t)(U2_A_BOX_ROWS * 128);
-                for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
-                    int m = tile / P.nblk;
-                    const int kx = m % P.tiles_x;
-                    m /= P.tiles_x;
-                    const int ky = m % P.tiles_y;
-                    const int n = m / P.tiles_y;
+                for (int tile = walk.first; tile < walk.total; tile += walk.step) {
+                    int nb, kx, ky, n;
+                    u2_decode(P, walk, tile, nb, kx, ky, n);      // an invalid tile has n >= N: the TMA unit zero-fills the box
                     const int x0 = U2_STEP_J * kx - 2, y0 = U2_STEP_I * ky - 2;     // box origin = tile origin - 1 (halo)
                     for (int ks = 0; ks < kslabs; ++ks) {
                         mbar_wait(&a_empty[buf], phase ^ 1);
@@ -177,7 +230,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
             // ===================== weight TMA producer =====================
             if (elect_one()) {
                 uint32_t phase = 0;          // the four regions are used in lock step: one phase bit serves all
-                for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
+                for (int tile = walk.first; tile < walk.total; tile += walk.step) {
                     const int nb = tile % P.nblk;
                     for (int ks = 0; ks < kslabs; ++ks) {
                         for (int h = 0; h < nplanes; ++h) {
@@ -185,10 +238,14 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
 #pragma unroll 1
                             for (int sg = 0; sg < 4; ++sg) {
                                 mbar_wait(&w_empty[sg], phase ^ 1);
+                                // the whole region arrives in this CTA's shared memory whoever loads it
                                 mbar_expect_tx(&w_full[sg], (uint32_t)(P.sg_units[sg] * U2_W_UNIT));
                                 for (int u = 0; u < P.sg_units[sg]; ++u) {
                                     const int unit = P.sg_ubase[sg] + u;
-                                    tma_load_2d(w_base + unit * U2_W_UNIT, wm, &w_full[sg], ks * U2_KC, nb * U2_ROWS_PER_NBLK + unit * 64);
+                                    if (!walk.cluster)
+                                        tma_load_2d(w_base + unit * U2_W_UNIT, wm, &w_full[sg], ks * U2_KC, nb * U2_ROWS_PER_NBLK + unit * 64);
+                                    else if ((unit & 1) == walk.rank)       // units 0,2,4,6,8 by rank 0; 1,3,5,7 by rank 1
+                                        u2_tma_load_2d_mc(w_base + unit * U2_W_UNIT, wm, &w_full[sg], ks * U2_KC, nb * U2_ROWS_PER_NBLK + unit * 64);
                                 }
                             }
                             phase ^= 1;
@@ -202,14 +259,10 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
             // global memory; this otherwise idle warp pulls the NEXT tile's lines into L2 so that those loads are L2 hits.
             if (epi.skip_hi || epi.noise) {
                 int k = 1;
-                for (int tile = blockIdx.x + gridDim.x; tile < P.total; tile += gridDim.x, ++k) {
+                for (int tile = walk.first + walk.step; tile < walk.total; tile += walk.step, ++k) {
                     while (*epi_progress < k - 1) __nanosleep(500);     // stay exactly one tile ahead of the epilogue
-                    int m = tile / P.nblk;
-                    const int nb = tile - m * P.nblk;
-                    const int kx = m % P.tiles_x;
-                    m /= P.tiles_x;
-                    const int ky = m % P.tiles_y;
-                    const int n = m / P.tiles_y;
+                    int nb, kx, ky, n;
+                    if (!u2_decode(P, walk, tile, nb, kx, ky, n)) continue;
                     for (int i = lane; i < U2_OWN_Y * U2_OWN_X; i += 32) {
                         const int oy = i / U2_OWN_X, oxx = i - oy * U2_OWN_X;
                         const int y = U2_OWN_Y * ky + oy, x = U2_OWN_X * kx + oxx;
@@ -234,7 +287,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                 constexpr uint32_t A_PLANE16 = U2_A_PLANE >> 4, K16 = 32 >> 4;
                 int buf = 0, acc = 0;
                 uint32_t a_phase = 0, w_phase = 0, acc_phase = 0;
-                for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x) {
+                for (int tile = walk.first; tile < walk.total; tile += walk.step) {
                     for (int ks = 0; ks < kslabs; ++ks) {
                         const bool chunk_first = ks % P.chunk_slabs == 0, chunk_last = (ks + 1) % P.chunk_slabs == 0;
                         if (chunk_first) mbar_wait(&t_empty[acc], acc_phase ^ 1);
@@ -259,7 +312,8 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
                                     if (h == 0 && nplanes == 2)
                                         umma_f16(dcol, ((uint64_t)DESC_HI << 32) | (al + aoff16 + k * K16), db, idesc, 1);
                                 }
-                                umma_commit(&w_empty[sg]);
+                                if (walk.cluster) u2_commit_both(&w_empty[sg]);
+                                else umma_commit(&w_empty[sg]);
                             }
                             w_phase ^= 1;
                         }
@@ -304,17 +358,14 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
         int acc = 0;
         uint32_t acc_phase = 0;
         int tile_iter = 0;
-        for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x, ++tile_iter) {
-            int m = tile / P.nblk;
-            const int nb = tile - m * P.nblk;
-            const int kx = m % P.tiles_x;
-            m /= P.tiles_x;
-            const int ky = m % P.tiles_y;
-            const int n = m / P.tiles_y;
+        for (int tile = walk.first; tile < walk.total; tile += walk.step, ++tile_iter) {
+            int nb, kx, ky, n;
+            const bool tile_valid = u2_decode(P, walk, tile, nb, kx, ky, n);
+            if (!tile_valid) n = 0;            // (keeps the staged per-sample vectors in bounds; nothing of this tile is stored)
             if (e == 0) *epi_progress = tile_iter;
             const int y0 = U2_OWN_Y * ky + 6 * hr, x = U2_OWN_X * kx + ox;     // my first output row, my output column
             const int rows_valid = P.OH - y0 < 6 ? P.OH - y0 : 6;              // (may be <= 0)
-            const bool col_valid = blur_active && x < P.OW && rows_valid > 0;
+            const bool col_valid = tile_valid && blur_active && x < P.OW && rows_valid > 0;
 
             mbar_wait(&t_full[acc], acc_phase);
             tc_fence_after();
@@ -444,13 +495,10 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
         int acc = 0;
         uint32_t acc_phase = 0;
         int tile_iter = 0;
-        for (int tile = blockIdx.x; tile < P.total; tile += gridDim.x, ++tile_iter) {
-            int m = tile / P.nblk;
-            const int nb = tile - m * P.nblk;
-            const int kx = m % P.tiles_x;
-            m /= P.tiles_x;
-            const int ky = m % P.tiles_y;
-            const int n = m / P.tiles_y;
+        for (int tile = walk.first; tile < walk.total; tile += walk.step, ++tile_iter) {
+            int nb, kx, ky, n;
+            const bool tile_valid = u2_decode(P, walk, tile, nb, kx, ky, n);
+            if (!tile_valid) n = 0;            // (keeps the staged per-sample vectors in bounds; nothing of this tile is stored)
             if (e == 0) *epi_progress = tile_iter;
 
             float accv[128];
@@ -474,7 +522,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
 
             const int y0 = U2_OWN_Y * ky, x = U2_OWN_X * kx + ox;       // first output row of the tile, my output column
             const int rows_valid = P.OH - y0 < U2_OWN_Y ? P.OH - y0 : U2_OWN_Y;
-            const bool col_valid = blur_active && x < P.OW;
+            const bool col_valid = tile_valid && blur_active && x < P.OW;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 // the z tile / staging area is free again (previous round's or tile's readers are done)
@@ -582,6 +630,7 @@ conv_up2_kernel(const __grid_constant__ Up2Tmaps maps, const __grid_constant__ U
 
     tc_fence_before();
     __syncthreads();
+    if (P.cluster) u2_cluster_sync_all();        // no CTA leaves while the peer may still write its shared memory / signal its barriers
     tc_fence_after();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -600,7 +649,7 @@ extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
     SHGAN_CHECK(d->C >= 64 && d->C % 64 == 0 && d->Co >= 64 && d->Co % 64 == 0, "C and Co must be multiples of 64");
     SHGAN_CHECK((long long)d->N * d->C * d->H * d->W <= INT32_MAX, "input tensor is too large");
     SHGAN_CHECK(4LL * d->N * d->Co * d->H * d->W <= INT32_MAX, "output tensor is too large");
-    const int passes_arg = d->passes & ~SHGAN_UP2_NARROW;
+    const int passes_arg = d->passes & ~(SHGAN_UP2_NARROW | SHGAN_UP2_CLUSTER | SHGAN_UP2_NO_CLUSTER);
     SHGAN_CHECK(passes_arg == 0 || passes_arg == 1 || passes_arg == 3, "passes must be 0, 1 or 3");
     if (const char* m = check_epi(d->epi, d->Co)) SHGAN_CHECK(false, m);
     SHGAN_CHECK(!d->epi.rgb_w, "the up-sampling convolution has no fused torgb");
@@ -612,9 +661,11 @@ extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
     P.tiles_x = ceil_div(P.OW, U2_OWN_X);
     P.tiles_y = ceil_div(P.OH, U2_OWN_Y);
     P.nblk = d->Co / 64;
-    const long long total = (long long)P.tiles_x * P.tiles_y * d->N * P.nblk;
-    SHGAN_CHECK(total <= INT32_MAX, "too many tiles");
-    P.total = (int)total;
+    const long long total_m = (long long)P.tiles_x * P.tiles_y * d->N;
+    SHGAN_CHECK(total_m * P.nblk <= INT32_MAX, "too many tiles");
+    P.total_m = (int)total_m;
+    P.cluster = 0;
+    P.total = (int)(total_m * P.nblk);
     for (int i = 0; i < 4; ++i) { P.fx[i] = d->fx[i]; P.fy[i] = d->fy[i] * d->gain; }
     P.acc_comp = d->acc_comp == 0.f ? SHGAN_ACC_COMP_DEFAULT : (d->acc_comp < 0.f ? 0.f : d->acc_comp);
     P.passes = passes_arg == 0 ? 3 : passes_arg;
@@ -650,10 +701,32 @@ extern "C" int shgan_conv_up2(const shgan_up2_desc* d, void* stream_) {
             SHGAN_CUDA(cudaFuncSetAttribute(conv_up2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
             return 0;
         })) return e;
-    const int grid = P.total < num_sms ? P.total : num_sms;
+    // Clusters of two CTAs that share each weight load by TMA multicast: only on request.  Measured on B200 (batch 16, C = 256 / 512
+    // layers, profiles/r2_up2_findings.md): 0.695 / 0.646 / 0.431 ms with, 0.699 / 0.654 / 0.427 ms without -- halving the weight
+    // requests changes nothing, so these layers are bound by the LATENCY of the single-buffered weight regions, not by L2 -> SM bytes.
+    const bool cluster = (d->passes & SHGAN_UP2_CLUSTER) && !(d->passes & SHGAN_UP2_NO_CLUSTER);
+    int grid = P.total < num_sms ? P.total : num_sms;
+    if (cluster) {
+        P.cluster = 1;
+        P.total = (int)((total_m + 1) / 2) * P.nblk;        // virtual tiles walked by a pair
+        const int pairs = P.total < num_sms / 2 ? P.total : num_sms / 2;
+        grid = 2 * pairs;
+    }
     const EpiParams epi = make_epi(d->epi);
-    if (wide) conv_up2_kernel<true><<<grid, U2Cfg<true>::THREADS, U2_SMEM_BYTES, stream>>>(maps, P, epi);
-    else conv_up2_kernel<false><<<grid, U2Cfg<false>::THREADS, U2_SMEM_BYTES, stream>>>(maps, P, epi);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)(wide ? U2Cfg<true>::THREADS : U2Cfg<false>::THREADS), 1, 1);
+    cfg.dynamicSmemBytes = U2_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster ? 1 : 0;
+    if (wide) SHGAN_CUDA(cudaLaunchKernelEx(&cfg, conv_up2_kernel<true>, maps, P, epi));
+    else SHGAN_CUDA(cudaLaunchKernelEx(&cfg, conv_up2_kernel<false>, maps, P, epi));
     SHGAN_LAUNCH_CHECK();
     return 0;
 }

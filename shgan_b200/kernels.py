@@ -233,10 +233,11 @@ UP2_NARROW = 0x100      # SHGAN_UP2_NARROW
 
 
 @_on_tensor_device
-def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None, narrow=False):
+def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None, narrow=False, cluster=None):
     """Fused up-sampling convolution (shgan_conv_up2): src Planes [N,H,W,C]; w_hi/w_lo fp16 [Co/64, 9, 64, C] from
     packing.pack_up2_weight; fx/fy: the separable blur taps as applied (4 floats each); epi: Epilogue at [N,2H,2W,Co].
-    narrow=True forces the 8-warp epilogue instance (tests / profiling)."""
+    narrow=True forces the 8-warp epilogue instance, cluster=True / False forces / forbids the two-CTA weight-sharing clusters
+    (tests / profiling; None = the library's choice)."""
     d = Up2Desc()
     n, h, w, c = src.shape
     d.src_hi = _p(src.hi); d.src_lo = _p(src.lo)
@@ -246,7 +247,7 @@ def conv_up2(src, w_hi, w_lo, fx, fy, gain, epi, passes=3, acc_comp=None, narrow
         d.fx[i] = float(fx[i]); d.fy[i] = float(fy[i])
     d.gain = float(gain)
     d.epi = epi
-    d.passes = passes | (UP2_NARROW if narrow else 0)
+    d.passes = passes | (UP2_NARROW if narrow else 0) | (0 if cluster is None else (0x200 if cluster else 0x400))
     d.acc_comp = ACC_COMP if acc_comp is None else acc_comp
     lib = _lib.load()
     _lib.check(lib.shgan_conv_up2(C.byref(d), _stream()), 'shgan_conv_up2')

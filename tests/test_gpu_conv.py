@@ -305,8 +305,11 @@ UP2_SHAPES = [(2, 64, 64, 8, 8), (1, 128, 64, 20, 23), (2, 64, 128, 13, 7), (1, 
 @pytest.mark.parametrize('shape', UP2_SHAPES, ids=[str(s) for s in UP2_SHAPES])
 @pytest.mark.parametrize('passes', [3, 1])
 @pytest.mark.parametrize('narrow', [False, True], ids=['auto', 'narrow'])
-def test_conv_up2_tc_vs_fp64(shape, passes, narrow):
-    """Both epilogue instances of the fused kernel: C <= 256 runs the 16-warp one unless `narrow` forces the 8-warp one."""
+@pytest.mark.parametrize('cluster', [False, True], ids=['single', 'pair'])
+def test_conv_up2_tc_vs_fp64(shape, passes, narrow, cluster):
+    """Both epilogue instances of the fused kernel (C <= 256 runs the 16-warp one unless `narrow` forces the 8-warp one), each as
+    single CTAs and as two-CTA clusters sharing every weight load by TMA multicast (odd tile counts leave one CTA of the last
+    pair with an invalid tile)."""
     from shgan_b200 import kernels as K, packing as P
     n, ci, co, h, wd = shape
     if narrow and ci > 256:
@@ -322,7 +325,7 @@ def test_conv_up2_tc_vs_fp64(shape, passes, narrow):
     uh, ul = P.pack_up2_weight(w)
     # raw accumulator path (identity epilogue)
     y32 = torch.empty((n, 2 * h, 2 * wd, co), device=DEV)
-    K.conv_up2(xp, uh, ul, fx, fy, 4.0 / 49.0, K.make_epilogue(out_f32=y32), passes=passes, narrow=narrow)
+    K.conv_up2(xp, uh, ul, fx, fy, 4.0 / 49.0, K.make_epilogue(out_f32=y32), passes=passes, narrow=narrow, cluster=cluster)
     tol = 1e-5 if passes == 3 else 5e-3
     assert relerr(y32.permute(0, 3, 1, 2).cpu().numpy(), ref.cpu().numpy()) <= tol
     # full epilogue: demod, per-sample noise, bias, lrelu + clamp, skip, next-layer style; planes + fp32 outputs
@@ -336,7 +339,7 @@ def test_conv_up2_tc_vs_fp64(shape, passes, narrow):
     K.conv_up2(xp, uh, ul, fx, fy, 4.0 / 49.0,
                K.make_epilogue(dcoef=dc, wgain=0.7, noise=nzv, noise_sn=4 * h * wd, noise_strength=strength, bias=bias, act=True,
                                act_alpha=0.2, act_gain=2 ** 0.5, act_clamp=3.0, skip=K.nchw_to_planes(skip), next_scale=ns, out=out,
-                               out_f32=y32), passes=passes, narrow=narrow)
+                               out_f32=y32), passes=passes, narrow=narrow, cluster=cluster)
     v = ref * dc[:, :, None, None] * 0.7 + nzv * 0.3 + bias[None, :, None, None]
     v = (torch.where(v >= 0, v, v * 0.2) * 2 ** 0.5).clamp(-3.0, 3.0)
     sk = K.planes_to_nchw(K.nchw_to_planes(skip)).double()

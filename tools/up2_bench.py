@@ -10,8 +10,10 @@ from shgan_b200 import kernels as K, packing as P  # noqa: E402
 
 dev = 'cuda'
 LAYERS = {'b512': (16, 128, 64, 256), 'b256': (16, 256, 128, 128), 'b128': (16, 512, 256, 64), 'b64': (16, 512, 512, 32)}
+LAYERS['b32'] = (16, 512, 512, 16)
 which = [a for a in sys.argv[1:] if a in LAYERS] or list(LAYERS)
 NARROW = 'narrow' in sys.argv       # force the 8-warp epilogue instance
+CLUSTER = True if 'cluster' in sys.argv else (False if 'nocluster' in sys.argv else None)     # force / forbid the weight-sharing CTA pairs
 NO_SKIP = 'noskip' in sys.argv      # experiment: epilogue without the skip planes / the noise (how much do their loads cost?)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name in which:
@@ -32,7 +34,7 @@ for name in which:
     epi = K.make_epilogue(dcoef=dc, noise=None if NO_SKIP else nz, noise_sn=4 * h * h, noise_strength=st, bias=bias, act=True, act_gain=2 ** 0.5,
                           act_clamp=256.0, skip=None if NO_SKIP else skip, next_scale=ns, out=out)
     fy = fx = [0.125, 0.375, 0.375, 0.125]
-    run = lambda: K.conv_up2(x, uh, ul, fx, fy, 4.0, epi, narrow=NARROW)
+    run = lambda: K.conv_up2(x, uh, ul, fx, fy, 4.0, epi, narrow=NARROW, cluster=CLUSTER)
     for _ in range(3):
         run()
     ts = []
