@@ -197,6 +197,10 @@ int shgan_conv_up2(const shgan_up2_desc* d, void* stream);
  * [1,3,3,1] blur is).  Without the flag the library decides on the device, and a second, general-filter kernel is always
  * launched behind the separable one (it returns at once for rank-1 filters); with it that launch is skipped. */
 #define SHGAN_FIR_RANK1 0x100
+/* parity_split | SHGAN_FIR_TWO_PHASE: with SHGAN_FIR_RANK1, planes input and an identity epilogue (the blur in front of the
+ * stride-2 convolutions) the library runs a row-walking kernel; this flag selects the TMA-staged two-phase kernel instead
+ * (tests, profiling). */
+#define SHGAN_FIR_TWO_PHASE 0x200
 int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void* in_lo,
                    const float* f, int fH, int fW, float gain,
                    int N, int C, int IH, int IW, int pad_x0, int pad_x1, int pad_y0, int pad_y1,

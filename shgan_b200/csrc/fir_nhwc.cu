@@ -511,6 +511,152 @@ fir4x4_2p_kernel(const __grid_constant__ FirMaps maps, const float* __restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-walking separable kernel for the blur in front of the stride-2 convolutions (planes in -> blurred planes out, identity
+// epilogue, the caller vouches for a rank-1 filter): the hot use of this entry point (7 launches per generator step).
+// The two-phase kernel above issues ~25 instructions per output element at 16 warps per SM with two block barriers per tile
+// (measured: 0.39-0.50 of HBM, issue-limited at ~1.1 IPC).  Here nothing synchronises wider than a warp:
+//   * a warp owns 8 output columns x 32 channels (lane = column x 8-channel group) and walks down a segment of FW_SEG output
+//     rows; every input row is loaded once (11 pixel vectors per warp: 128-bit loads of both planes, the NEXT row requested
+//     before the current one is consumed), converted to fp32 once and passed through a per-warp shared-memory row
+//     ([half][pixel][group][4 floats]: conflict-free 128-bit stores and loads) so that a lane reads the 4 pixels of its output;
+//   * horizontal 4-tap pass (32 FMA per lane and row) into a ring of the last four horizontal rows in registers (rotated
+//     statically over a 4x unrolled loop), vertical pass (32 FMA), hi/lo split, two 128-bit stores into the parity planes.
+constexpr int FW_PX = 8, FW_CG = 4, FW_SEG = 32, FW_NPIX = FW_PX + FIR_T - 1;
+constexpr int FW_HALF = FW_NPIX * FW_CG * 4;          // floats per half row buffer (channels 0-3 | 4-7 of every group)
+constexpr int FW_ROWBUF = 2 * FW_HALF;                // 352 floats
+constexpr int FW_STAGES = 4;                          // raw input rows in flight per warp (cp.async ring)
+constexpr int FW_RAW_PLANE = FW_NPIX * FW_CG * 16;    // bytes of one plane of one raw row: 704
+constexpr int FW_RAW_STAGE = 2 * FW_RAW_PLANE;
+constexpr int FW_WARP_BYTES = 2 * FW_ROWBUF * 4 + FW_STAGES * FW_RAW_STAGE;      // 2816 + 5632
+constexpr int FW_SMEM_BYTES = 8 * FW_WARP_BYTES + 64;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+fir4x4_walk_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, const float* __restrict__ f, float gain,
+                   int N, int C, int IH, int IW, int OH, int OW, int pad_x0, int pad_y0, __half* __restrict__ out_hi,
+                   __half* __restrict__ out_lo, int parity_split, int xblocks, int segs, int cblocks, int items) {
+    extern __shared__ __align__(16) uint8_t fw_smem[];
+    __shared__ float s_f[FIR_T * FIR_T];
+    if (threadIdx.x < FIR_T * FIR_T) s_f[threadIdx.x] = f[threadIdx.x];
+    __syncthreads();
+    float u[FIR_T], v[FIR_T];
+    fir_factorise(s_f, u, v);                    // (the caller vouches for rank 1)
+#pragma unroll
+    for (int i = 0; i < FIR_T; ++i) u[i] *= gain;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 8 + warp;
+    if (item >= items) return;
+    int t = item;
+    const int cb = t % cblocks; t /= cblocks;
+    const int xb = t % xblocks; t /= xblocks;
+    const int seg = t % segs;
+    const int n = t / segs;
+    const int xl = lane >> 2, cg = lane & 3;
+    const int c0 = cb * 32 + cg * 8;
+    const int x = xb * FW_PX + xl;                         // my output column
+    const int ix0 = xb * FW_PX - pad_x0;                   // input column of pixel 0 of the row buffer
+    const int oy0 = seg * FW_SEG, oy1 = min(OH, oy0 + FW_SEG);
+    const int PH = (OH + 1) / 2, PW = (OW + 1) / 2;
+    const size_t in_n = (size_t)n * IH * IW;
+    uint8_t* wbase = fw_smem + warp * FW_WARP_BYTES;
+    float* rowbuf = reinterpret_cast<float*>(wbase);                         // [2][FW_ROWBUF]
+    const uint32_t raw0 = smem_u32(wbase + 2 * FW_ROWBUF * 4);                // [FW_STAGES][2 planes][11 pixels][4 groups] x 16 B
+    const int ia = ix0 + xl, ib = ix0 + FW_PX + xl;
+    const bool va = ia >= 0 && ia < IW, vb = xl < FIR_T - 1 && ib >= 0 && ib < IW;
+    const uint32_t offa = (uint32_t)((xl * FW_CG + cg) * 16), offb = (uint32_t)(((FW_PX + xl) * FW_CG + cg) * 16);
+
+    // one input row -> the warp's raw ring, straight from global memory (zero-filled outside the image): no registers held
+    // while up to three rows are in flight
+    auto request_row = [&](int iy, int stage) {
+        const bool rv = iy >= 0 && iy < IH;
+        const size_t rowbase = (in_n + (size_t)(rv ? iy : 0) * IW) * C + c0;
+        const uint32_t d = raw0 + (uint32_t)stage * FW_RAW_STAGE;
+        const size_t ea = rowbase + (size_t)(va ? ia : 0) * C, eb = rowbase + (size_t)(vb ? ib : 0) * C;
+        cp_async16(d + offa, in_hi + ea, rv && va);
+        cp_async16(d + FW_RAW_PLANE + offa, in_lo + ea, rv && va);
+        if (xl < FIR_T - 1) {
+            cp_async16(d + offb, in_hi + eb, rv && vb);
+            cp_async16(d + FW_RAW_PLANE + offb, in_lo + eb, rv && vb);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto unpack_store = [&](uint32_t src, float* rb, int pix) {
+        const uint4 h = lds128(src), l = lds128(src + FW_RAW_PLANE);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 fa = unpack_h2(hw[i]), fb = unpack_h2(lw[i]);
+            e[2 * i] = fa.x + fb.x;
+            e[2 * i + 1] = fa.y + fb.y;
+        }
+        float* d = rb + (pix * FW_CG + cg) * 4;
+        *reinterpret_cast<float4*>(d) = make_float4(e[0], e[1], e[2], e[3]);
+        *reinterpret_cast<float4*>(d + FW_HALF) = make_float4(e[4], e[5], e[6], e[7]);
+    };
+    // horizontal pass of the oldest requested row (every lane converts the pixel vectors it requested itself, the fp32 row is
+    // exchanged through the per-warp buffer): my output column reads pixels xl .. xl+3
+    auto hpass = [&](int stage, int b, float (&h)[8]) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(FW_STAGES - 1) : "memory");
+        float* rb = rowbuf + b * FW_ROWBUF;
+        const uint32_t src = raw0 + (uint32_t)stage * FW_RAW_STAGE;
+        unpack_store(src + offa, rb, xl);
+        if (xl < FIR_T - 1) unpack_store(src + offb, rb, FW_PX + xl);
+        __syncwarp();
+        const float* s = rb + (xl * FW_CG + cg) * 4;
+#pragma unroll
+        for (int j = 0; j < FIR_T; ++j) {
+            const float4 a = *reinterpret_cast<const float4*>(s + j * FW_CG * 4);
+            const float4 c = *reinterpret_cast<const float4*>(s + j * FW_CG * 4 + FW_HALF);
+            if (j == 0) {
+                h[0] = v[0] * a.x; h[1] = v[0] * a.y; h[2] = v[0] * a.z; h[3] = v[0] * a.w;
+                h[4] = v[0] * c.x; h[5] = v[0] * c.y; h[6] = v[0] * c.z; h[7] = v[0] * c.w;
+            } else {
+                h[0] = fmaf(v[j], a.x, h[0]); h[1] = fmaf(v[j], a.y, h[1]); h[2] = fmaf(v[j], a.z, h[2]); h[3] = fmaf(v[j], a.w, h[3]);
+                h[4] = fmaf(v[j], c.x, h[4]); h[5] = fmaf(v[j], c.y, h[5]); h[6] = fmaf(v[j], c.z, h[6]); h[7] = fmaf(v[j], c.w, h[7]);
+            }
+        }
+    };
+    auto emit = [&](int oy, const float (&ha)[8], const float (&hb)[8], const float (&hc)[8], const float (&hd)[8]) {
+        if (oy >= oy1 || x >= OW) return;
+        if (parity_split == 2 && ((oy | x) & 1)) return;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(u[3], hd[i], fmaf(u[2], hc[i], fmaf(u[1], hb[i], u[0] * ha[i])));
+        size_t pix;
+        if (parity_split == 1) pix = (size_t)((oy & 1) * 2 + (x & 1)) * N * PH * PW + ((size_t)n * PH + (oy >> 1)) * PW + (x >> 1);
+        else if (parity_split == 2) pix = ((size_t)n * PH + (oy >> 1)) * PW + (x >> 1);
+        else pix = ((size_t)n * OH + oy) * OW + x;
+        store_planes8(out_hi, out_lo, (long long)(pix * C + c0), o);
+    };
+
+    // output row oy = sum_k u[k] * hrow(oy - pad_y0 + k).  Row r of the walk (r = 0 is input row oy0 - pad_y0) lives in raw stage
+    // r & 3 and row buffer r & 1; three rows are always requested ahead of the one being consumed.
+    float h0[8], h1[8], h2[8], h3[8];
+    int iy = oy0 - pad_y0;
+    request_row(iy, 0);
+    request_row(iy + 1, 1);
+    request_row(iy + 2, 2);
+    request_row(iy + 3, 3); hpass(0, 0, h0);
+    request_row(iy + 4, 0); hpass(1, 1, h1);
+    request_row(iy + 5, 1); hpass(2, 0, h2);
+    iy += 6;                                               // next row to request; the next row to consume is in stage 3
+#pragma unroll 1
+    for (int oy = oy0; oy < oy1; oy += 4) {
+        request_row(iy, 2);     hpass(3, 1, h3); emit(oy, h0, h1, h2, h3);
+        request_row(iy + 1, 3); hpass(0, 0, h0); emit(oy + 1, h1, h2, h3, h0);
+        request_row(iy + 2, 0); hpass(1, 1, h1); emit(oy + 2, h2, h3, h0, h1);
+        request_row(iy + 3, 1); hpass(2, 0, h2); emit(oy + 3, h3, h0, h1, h2);
+        iy += 4;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 }  // namespace shgan
 
 using namespace shgan;
@@ -528,7 +674,8 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
     if (const char* m = check_epi(*epi_, C)) SHGAN_CHECK(false, m);
     SHGAN_CHECK(!epi_->rgb_w, "fused torgb is not available in the FIR epilogue");
     const bool rank1_hint = (parity_split & SHGAN_FIR_RANK1) != 0;
-    parity_split &= ~SHGAN_FIR_RANK1;
+    const bool force_two_phase = (parity_split & SHGAN_FIR_TWO_PHASE) != 0;
+    parity_split &= ~(SHGAN_FIR_RANK1 | SHGAN_FIR_TWO_PHASE);
     SHGAN_CHECK(parity_split >= 0 && parity_split <= 2, "parity_split must be 0, 1 or 2");
     SHGAN_CHECK(!parity_split || (!epi_->out_f32 && !epi_->skip_hi && !epi_->noise), "parity_split supports plane output only");
     SHGAN_CHECK((long long)N * C * ((long long)OH + 1) * (OW + 1) <= INT32_MAX, "tensor is too large");
@@ -539,12 +686,26 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
     if (int e = device_init(once, &num_sms, []() -> int {
             SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
             SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
+            SHGAN_CUDA(cudaFuncSetAttribute(fir4x4_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES));
             return 0;
         })) return e;
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)IW, (uint64_t)IH, (uint64_t)N};
     int skip_rank1 = 0;
     // measured on B200, batch 16, 64 channels @512^2: planes input (encoder down path) 0.78 ms two-phase vs 0.91 ms TMA-staged
     // general kernel; fp32 input + full epilogue (synthesis up path) 1.33 ms two-phase vs 1.05 ms register kernel
+    const bool identity_epi = !epi.dcoef && epi.wgain == 1.f && !epi.noise && !epi.bias && !epi.act && epi.act_gain == 1.f && !epi.skip_hi &&
+                              !epi.next_scale && !epi.out_f32 && epi.out_hi && epi.out_lo;
+    if (rank1_hint && identity_epi && !in_f32 && C % 32 == 0 && !force_two_phase) {
+        // the blur in front of the stride-2 convolutions (planes -> planes): row-walking kernel, no block barriers
+        const int xblocks = ceil_div(OW, FW_PX), segs = ceil_div(OH, FW_SEG), cblocks = C / 32;
+        const long long items = (long long)xblocks * segs * cblocks * N;
+        SHGAN_CHECK(items <= INT32_MAX, "too many work items");
+        fir4x4_walk_kernel<<<(unsigned)ceil_div64(items, 8), 256, FW_SMEM_BYTES, (cudaStream_t)stream>>>(
+            (const __half*)in_hi, (const __half*)in_lo, f, gain, N, C, IH, IW, OH, OW, pad_x0, pad_y0, epi.out_hi, epi.out_lo, parity_split,
+            xblocks, segs, cblocks, (int)items);
+        SHGAN_LAUNCH_CHECK();
+        return 0;
+    }
     if (C % F2_C == 0 && !in_f32) {
         // rank-1 filters (the reference's): two-phase separable kernel; it returns immediately for any other filter, and the
         // general kernel launched below returns immediately for rank-1 filters (the test runs on the device: no host sync)

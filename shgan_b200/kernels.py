@@ -260,10 +260,14 @@ def conv_num_nblocks(co, block_n=0):
 FIR_RANK1 = 0x100
 
 
+FIR_TWO_PHASE = 0x200   # SHGAN_FIR_TWO_PHASE
+
+
 @_on_tensor_device
-def fir_nhwc(src, f, gain, pads, epi, parity_split=False, rank1=False):
+def fir_nhwc(src, f, gain, pads, epi, parity_split=False, rank1=False, two_phase=False):
     """src: Planes or fp32 NHWC tensor; pads = (pad_x0, pad_x1, pad_y0, pad_y1); f: fp32 [4,4] (as applied).
-    rank1=True: the caller has checked (on the host, once) that f is separable -> no fallback launch (SHGAN_FIR_RANK1)."""
+    rank1=True: the caller has checked (on the host, once) that f is separable -> no fallback launch (SHGAN_FIR_RANK1);
+    with planes in and an identity epilogue that is the row-walking kernel unless two_phase=True (tests, profiling)."""
     lib = _lib.load()
     if isinstance(src, Planes):
         n, ih, iw, c = src.shape
@@ -273,7 +277,7 @@ def fir_nhwc(src, f, gain, pads, epi, parity_split=False, rank1=False):
         n, ih, iw, c = src.shape
         args = (_p(src), None, None)
     _lib.check(lib.shgan_fir_nhwc(*args, _p(f), f.shape[0], f.shape[1], float(gain), n, c, ih, iw,
-                                 pads[0], pads[1], pads[2], pads[3], C.byref(epi), int(parity_split) | (FIR_RANK1 if rank1 else 0), _stream()),
+                                 pads[0], pads[1], pads[2], pads[3], C.byref(epi), int(parity_split) | (FIR_RANK1 if rank1 else 0) | (FIR_TWO_PHASE if two_phase else 0), _stream()),
                'shgan_fir_nhwc')
 
 

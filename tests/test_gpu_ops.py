@@ -237,6 +237,46 @@ def test_fir_nhwc_epilogue_and_parity():
             assert relerr(got[py * 2 + px][:, :, :sub.shape[2], :sub.shape[3]], sub) <= 3e-6
 
 
+@pytest.mark.parametrize('parity', [0, 1, 2])
+@pytest.mark.parametrize('shape,pads', [((2, 32, 11, 13), (2, 2, 2, 2)), ((1, 64, 70, 37), (2, 2, 2, 2)), ((3, 96, 40, 66), (1, 1, 1, 1)),
+                                        ((1, 128, 33, 9), (2, 1, 0, 3)), ((2, 64, 4, 4), (2, 2, 2, 2))], ids=str)
+def test_fir_walk_kernel(shape, pads, parity):
+    """The row-walking blur (planes -> planes, identity epilogue, rank-1 hint: the launch in front of every stride-2 conv) against
+    the oracle and, bit for bit up to fp32 summation order, against the two-phase kernel it replaces; asymmetric separable taps."""
+    from shgan_b200 import kernels as K
+    r = np.random.default_rng(shape[1] + shape[2])
+    f = np.outer([1.0, 2.0, 3.5, 0.5], [0.5, 3.0, 2.0, 1.5]).astype(np.float32) / 49
+    x = r.standard_normal(shape).astype(np.float32)
+    n, c, h, w = shape
+    oh, ow = h + pads[2] + pads[3] - 3, w + pads[0] + pads[1] - 3
+    xp = K.nchw_to_planes(t(x))
+    ft = t(f)
+    ref = O.upfirdn2d(x, f, padding=list(pads), flip_filter=True, gain=1.25)       # fir_nhwc applies f as given (correlation)
+    outs = []
+    for two_phase in (False, True):
+        if parity == 0:
+            out = K.Planes.empty(n, oh, ow, c, DEV)
+        elif parity == 1:
+            out = K.Planes.empty(4 * n, (oh + 1) // 2, (ow + 1) // 2, c, DEV)
+        else:
+            out = K.Planes.empty(n, (oh + 1) // 2, (ow + 1) // 2, c, DEV)
+        out.hi.zero_(); out.lo.zero_()
+        K.fir_nhwc(xp, ft, 1.25, pads, K.make_epilogue(out=out), parity_split=parity, rank1=True, two_phase=two_phase)
+        outs.append(K.planes_to_nchw(out).cpu().numpy())
+    got = outs[0]
+    if parity == 0:
+        assert relerr(got, ref) <= 3e-6
+    elif parity == 2:
+        assert relerr(got, ref[:, :, ::2, ::2]) <= 3e-6
+    else:
+        g4 = got.reshape(4, n, c, (oh + 1) // 2, (ow + 1) // 2)
+        for py in range(2):
+            for px in range(2):
+                sub = ref[:, :, py::2, px::2]
+                assert relerr(g4[py * 2 + px][:, :, :sub.shape[2], :sub.shape[3]], sub) <= 3e-6
+    assert relerr(outs[0], outs[1]) <= 3e-6          # same cells written (the rest stays zero in both), same values
+
+
 def test_fromrgb_and_torgb_combine():
     from shgan_b200 import kernels as K
     r = np.random.default_rng(6)

@@ -32,9 +32,10 @@ if 'fir' in which:
         ph = (H + 2) // 2
         par = K.Planes.empty(4 * N, ph, ph, C, dev)
         epi = K.make_epilogue(out=par)
-        us = timeit(lambda: K.fir_nhwc(src, f, 1.0, (2, 2, 2, 2), epi, parity_split=True), flush=flush)
         byts = N * H * H * C * 4 + N * (H + 1) ** 2 * C * 4
-        print(f'fir<planes,parity> N{N} {H}x{H}x{C}: {us:8.1f} us  {byts/us/1e3:.0f} GB/s')
+        for tp in (False, True):
+            us = timeit(lambda: K.fir_nhwc(src, f, 1.0, (2, 2, 2, 2), epi, parity_split=True, rank1=True, two_phase=tp), flush=flush)
+            print(f'fir<planes,parity,{"two-phase" if tp else "walk"}> N{N} {H}x{H}x{C}: {us:8.1f} us  {byts/us/1e3:.0f} GB/s')
         z = torch.randn(N, H + 1, H + 1, C, device=dev)
         out = K.Planes.empty(N, H, H, C, dev); skip = K.Planes.empty(N, H, H, C, dev)
         dc = torch.rand(N, C, device=dev); bias = torch.randn(C, device=dev); ns = torch.rand(N, C, device=dev)
