@@ -680,7 +680,7 @@ def main():
         )
         if fam_ms['fir'] > 0:
             gbs = fam['fir']['work'] / fam_ms['fir'] / 1e6
-            line['roofline_fir'] = dict(bound='hbm', kernel='shgan_fir_nhwc (blur in front of the stride-2 convs: fir4x4_2p_kernel)',
+            line['roofline_fir'] = dict(bound='hbm', kernel='shgan_fir_nhwc (blur in front of the stride-2 convs: fir4x4_walk_kernel)',
                                         achieved=gbs, peak=peaks['hbm'], unit='GB/s', frac=gbs / peaks['hbm'], traffic=None,
                                         peak_source=f'{peaks["src"]} HBM copy', launches_per_step=len(fam['fir']['events']) // steps,
                                         kernel_ms_per_step=fam_ms['fir'] / steps, algorithmic_mb_per_step=fam['fir']['work'] / steps / 1e6)

@@ -85,6 +85,61 @@ fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ mask, floa
     }
 }
 
+// Fast instance for the shapes the models use (CI = 3 / 4 input channels known at compile time, grid stride a multiple of the
+// channel groups per pixel so that a thread's 8 output channels never change): weights x gain and bias live in registers for
+// the whole kernel and the activation gain is folded into them (lrelu(v) * g == lrelu(v * g) for g > 0).  ncu on the generic
+// kernel above (profiles/r2_fromrgb_ncu.md): 300 issued instructions per 8 outputs -- every iteration re-read its 4x8 weights
+// from shared memory (93 % L1 pipe, short-scoreboard stalls) and ran the MAX_CI = 8 loop with half of it predicated off.
+template <int CI>
+__global__ void __launch_bounds__(256)
+fromrgb_fast_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ x_out, const float* __restrict__ w,
+                    const float* __restrict__ bias, float wgain, float act_alpha, float act_gain, float act_clamp,
+                    __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int Co, int HW) {
+    const unsigned cgs = (unsigned)Co / 8u, total_pix = (unsigned)N * (unsigned)HW;
+    const unsigned gstride = gridDim.x * blockDim.x;        // a multiple of cgs (host)
+    const unsigned gid0 = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned pix = gid0 / cgs;
+    const int cg = (int)(gid0 - pix * cgs);
+    const unsigned pstride = gstride / cgs;
+    float wr[CI][8], br[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        br[j] = bias ? __ldg(bias + cg * 8 + j) * act_gain : 0.f;
+#pragma unroll
+        for (int i = 0; i < CI; ++i) wr[i][j] = __ldg(w + (cg * 8 + j) * CI + i) * (wgain * act_gain);
+    }
+    const float clampv = act_clamp > 0.f ? act_clamp : __int_as_float(0x7f800000);
+    unsigned n = pix / (unsigned)HW, p = pix - n * (unsigned)HW;
+    for (; pix < total_pix; pix += pstride) {
+        float xin[CI];
+        if (mask) {
+            const float m = __ldg(mask + (size_t)n * HW + p);
+            xin[0] = m - 0.5f;
+#pragma unroll
+            for (int i = 1; i < CI; ++i) xin[i] = __ldg(x + ((size_t)n * (CI - 1) + (i - 1)) * HW + p) * m;
+            if (cg == 0) {
+#pragma unroll
+                for (int i = 0; i < CI; ++i) x_out[((size_t)n * CI + i) * HW + p] = xin[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CI; ++i) xin[i] = __ldg(x + ((size_t)n * CI + i) * HW + p);
+        }
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = br[j];
+#pragma unroll
+            for (int i = 0; i < CI; ++i) a = fmaf(xin[i], wr[i][j], a);
+            a = fmaxf(a, a * act_alpha);                                   // lrelu (0 <= alpha <= 1), gain already applied
+            v[j] = fminf(fmaxf(a, -clampv), clampv);
+        }
+        store_planes8(out_hi, out_lo, (long long)((size_t)pix * Co + cg * 8), v);
+        p += pstride;
+        while (p >= (unsigned)HW) { p -= (unsigned)HW; ++n; }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 torgb_combine_kernel(const float* __restrict__ img_prev, const float* __restrict__ rgb_partial, int n_blocks,
                      const float* __restrict__ bias, const float* __restrict__ f, float* __restrict__ img_out, int N, int H,
@@ -286,6 +341,28 @@ extern "C" int shgan_mbstd_append(const void* in_hi, const void* in_lo, void* ou
     return 0;
 }
 
+static int launch_fromrgb(const float* x, const float* mask, float* x_out, const float* w, const float* bias, float wgain, float act_alpha,
+                          float act_gain, float act_clamp, void* out_hi, void* out_lo, int N, int Ci, int Co, int HW, void* stream) {
+    const long long total = (long long)N * HW * (Co / 8);
+    long long blocks = ceil_div64(total, 256);
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    const int cgs = Co / 8;
+    // fast instance: 3 / 4 input channels, channel groups dividing the block size (so the grid stride is a multiple of them),
+    // the leaky-ReLU form max(v, alpha v) (0 <= alpha <= 1) and a positive gain (folded into the weights)
+    const bool fast = (Ci == 3 || Ci == 4) && 256 % cgs == 0 && act_alpha >= 0.f && act_alpha <= 1.f && act_gain > 0.f && (!mask || Ci >= 2);
+    if (fast && Ci == 4)
+        fromrgb_fast_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, mask, x_out, w, bias, wgain, act_alpha, act_gain, act_clamp,
+                                                                                   (__half*)out_hi, (__half*)out_lo, N, Co, HW);
+    else if (fast)
+        fromrgb_fast_kernel<3><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, mask, x_out, w, bias, wgain, act_alpha, act_gain, act_clamp,
+                                                                                   (__half*)out_hi, (__half*)out_lo, N, Co, HW);
+    else
+        fromrgb_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, mask, x_out, w, bias, wgain, act_alpha, act_gain, act_clamp,
+                                                                           (__half*)out_hi, (__half*)out_lo, N, Ci, Co, HW);
+    SHGAN_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int shgan_fromrgb(const float* x, const float* w, const float* bias, float wgain, float act_alpha,
                              float act_gain, float act_clamp, void* out_hi, void* out_lo, int N, int Ci, int Co, int H,
                              int W, void* stream) {
@@ -294,13 +371,7 @@ extern "C" int shgan_fromrgb(const float* x, const float* w, const float* bias, 
     SHGAN_CHECK(Co >= 8 && Co % 8 == 0 && Co <= FRGB_MAX_CO, "Co must be a multiple of 8, at most 128");
     SHGAN_CHECK(N >= 0 && H >= 1 && W >= 1 && (long long)N * Co * H * W <= INT32_MAX, "bad tensor size");
     if (N == 0) return 0;
-    const long long total = (long long)N * H * W * (Co / 8);
-    long long blocks = ceil_div64(total, 256);
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
-    fromrgb_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, w, bias, wgain, act_alpha, act_gain, act_clamp,
-                                                                       (__half*)out_hi, (__half*)out_lo, N, Ci, Co, H * W);
-    SHGAN_LAUNCH_CHECK();
-    return 0;
+    return launch_fromrgb(x, nullptr, nullptr, w, bias, wgain, act_alpha, act_gain, act_clamp, out_hi, out_lo, N, Ci, Co, H * W, stream);
 }
 
 extern "C" int shgan_fromrgb_masked(const float* real, const float* mask, float* x_out, const float* w, const float* bias,
@@ -311,13 +382,7 @@ extern "C" int shgan_fromrgb_masked(const float* real, const float* mask, float*
     SHGAN_CHECK(Co >= 8 && Co % 8 == 0 && Co <= FRGB_MAX_CO, "Co must be a multiple of 8, at most 128");
     SHGAN_CHECK(N >= 0 && H >= 1 && W >= 1 && (long long)N * Co * H * W <= INT32_MAX, "bad tensor size");
     if (N == 0) return 0;
-    const long long total = (long long)N * H * W * (Co / 8);
-    long long blocks = ceil_div64(total, 256);
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
-    fromrgb_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(real, mask, x_out, w, bias, wgain, act_alpha, act_gain, act_clamp,
-                                                                       (__half*)out_hi, (__half*)out_lo, N, Ci, Co, H * W);
-    SHGAN_LAUNCH_CHECK();
-    return 0;
+    return launch_fromrgb(real, mask, x_out, w, bias, wgain, act_alpha, act_gain, act_clamp, out_hi, out_lo, N, Ci, Co, H * W, stream);
 }
 
 extern "C" int shgan_torgb_combine(const float* img_prev, const float* rgb_partial, int n_blocks, const float* bias,

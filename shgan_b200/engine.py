@@ -573,6 +573,7 @@ class DiscriminatorEngine:
         self.res_list = list(D.encode_res)
         f = getattr(D, f'b{self.res_list[0]}').resample_filter
         self.f_applied = f.detach().to(dev, torch.float32).flip([0, 1]).contiguous()
+        self.f_rank1 = P.separable_taps(self.f_applied) is not None           # decided once on the host: no fallback launch, row-walking blur
         self.blocks = {}
 
         def conv(l, pad_ci=None):
@@ -637,7 +638,7 @@ class DiscriminatorEngine:
                 x = K.fromrgb(img, w, b, wg, self.act.alpha, self.act.gain, self.act.clamp, self._planes(f'd{r}.rgb', n, r, r, c))
             # skip: downsample2d (blur pad 1, keep even samples) -> 1x1 conv, no bias / activation, gain sqrt(1/2)
             ds = self._planes(f'd{r}.ds', n, r // 2, r // 2, c)
-            K.fir_nhwc(x, self.f_applied, 1.0, (1, 1, 1, 1), K.make_epilogue(out=ds), parity_split=2)
+            K.fir_nhwc(x, self.f_applied, 1.0, (1, 1, 1, 1), K.make_epilogue(out=ds), parity_split=2, rank1=self.f_rank1)
             y = self._planes(f'd{r}.skip', n, r // 2, r // 2, cn)
             conv([ds], d['skip'], P.taps_plain(1, 1), r // 2, r // 2, self._epi(d['skip'], y, gain=g, act=False))
             # conv0, then conv1 = blur (pad 2) into parity planes + stride-2 conv over them, gain sqrt(1/2), + skip
@@ -645,7 +646,7 @@ class DiscriminatorEngine:
             conv([x], d['conv0'], P.taps_plain(3, 3), r, r, self._epi(d['conv0'], t0))
             ph = (r + 2) // 2
             par = self._planes(f'd{r}.par', 4 * n, ph, ph, c)
-            K.fir_nhwc(t0, self.f_applied, 1.0, (2, 2, 2, 2), K.make_epilogue(out=par), parity_split=1)
+            K.fir_nhwc(t0, self.f_applied, 1.0, (2, 2, 2, 2), K.make_epilogue(out=par), parity_split=1, rank1=self.f_rank1)
             srcs = [Planes(par.hi[q * n:(q + 1) * n], par.lo[q * n:(q + 1) * n]) for q in range(4)]
             x = self._planes(f'd{r}.out', n, r // 2, r // 2, cn)
             conv(srcs, d['conv1'], P.taps_down2(3), r // 2, r // 2, self._epi(d['conv1'], x, gain=g, skip=y))
