@@ -242,7 +242,9 @@ int shgan_mbstd_append(const void* in_hi, const void* in_lo, void* out_hi, void*
 /* ---- dense / styles ------------------------------------------------------------------------
  * y[b,o] = act( (sum_i x[b,i] w[o,i]) * wgain + bias[o]*bgain )   replaces dense.forward
  * (torch.addmm), lib/model_zoo/stylegan.py:87-98.  x rows are read with stride x_stride floats;
- * x may be the concatenation [x0 (I0 floats) ; x1 (I-I0 floats)] (cat of comodgan.py:252,323). */
+ * x may be the concatenation [x0 (I0 floats) ; x1 (I-I0 floats)] (cat of comodgan.py:252,323).
+ * Layers with few outputs split I over a thread-block cluster; the partial sums are added in a fixed order
+ * (results are bit-identical from run to run). */
 int shgan_dense_fwd(const float* x0, int64_t x0_stride, int I0, const float* x1, int64_t x1_stride,
                     const float* w, const float* bias, float* y, int64_t y_stride,
                     int B, int I, int O, float wgain, float bgain,

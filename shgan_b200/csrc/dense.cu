@@ -16,11 +16,11 @@ constexpr int DCH = 512;  // input features per staged chunk: 4 x 128-bit weight
 
 // barrier over all threads of the thread-block cluster (release / acquire: shared-memory writes before it are visible to
 // distributed-shared-memory reads after it)
-__device__ __forceinline__ void cluster_sync_all() {
+__device__ __forceinline__ void dense_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // reads a float at the same shared-memory offset as `p` in the block of rank `rank` of this cluster
-__device__ __forceinline__ float ld_dsmem_f32(const float* p, int rank) {
+__device__ __forceinline__ float dense_ld_dsmem_f32(const float* p, int rank) {
     uint32_t remote;
     float v;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(rank));
@@ -120,18 +120,18 @@ dense_kernel(const float* __restrict__ x0, long long x0_stride, int I0, const fl
 #pragma unroll
             for (int j = 0; j < NB; ++j) { part[warp * 2][j] = acc0[j]; part[warp * 2 + 1][j] = acc1[j]; }
         }
-        if (KS > 1) cluster_sync_all(); else __syncthreads();
+        if (KS > 1) dense_cluster_sync(); else __syncthreads();
         if (blockIdx.x == 0 && threadIdx.x < DROWS * NB) {
             const int rr = threadIdx.x / NB, j = threadIdx.x % NB, oo = blockIdx.y * DROWS + rr;
             float v = part[rr][j];
-            for (int r = 1; r < KS; ++r) v += ld_dsmem_f32(&part[rr][j], r);      // fixed order: deterministic
+            for (int r = 1; r < KS; ++r) v += dense_ld_dsmem_f32(&part[rr][j], r);      // fixed order: deterministic
             if (oo < O && b0 + j < B) {
                 v = v * wgain + (bias ? __ldg(bias + oo) * bgain : 0.f);
                 if (act) v = lrelu_agc(v, act_alpha, act_gain, act_clamp);
                 y[(long long)(b0 + j) * y_stride + oo] = v;
             }
         }
-        if (KS > 1) cluster_sync_all();     // the peers' partials stay alive until the first block has read them
+        if (KS > 1) dense_cluster_sync();     // the peers' partials stay alive until the first block has read them
     }
 }
 
