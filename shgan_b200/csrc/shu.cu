@@ -69,7 +69,7 @@ __device__ __forceinline__ void fill_twiddles(float2* tw, int Lmax) {
 // dynamic smem: rowbuf [P][R/2][R] + colbuf [R][P][Rh] (planes interleaved per row: the P * Rh column transforms of a CTA are
 // then one uniformly strided batch) + tw [R/2] float2
 template <bool MULTI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 shu_rfft2_kernel(const float* __restrict__ x, float* __restrict__ spec1, int NC, int C, int R, int log2R, int P_) {
     extern __shared__ float2 sm[];
     const int P = MULTI ? P_ : 1;          // MULTI == false: one plane per CTA, the plane index below folds to 0 at compile time
@@ -184,7 +184,7 @@ shu_mix_kernel(const float* __restrict__ spec1, const float* __restrict__ conv0_
 
 // grid (ceil(N*C / P), num_bands), P planes per CTA; dynamic smem sized for the largest band: colbuf [r][P][rh] + rowbuf [P][r/2][r] + tw [R/2]
 template <bool MULTI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 shu_irfft2_kernel(const float* __restrict__ spec2, const float* __restrict__ gauss, ShuBands bands, int NC, int C, int R, int log2R, int P_) {
     extern __shared__ float2 sm[];
     const int P = MULTI ? P_ : 1;
@@ -438,12 +438,15 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     // 128 from the extra index arithmetic, hence R <= 16), as long as every SM still gets CTAs
     int fft_planes = 1;
     while (R <= 16 && fft_planes < 16 && (size_t)(2 * fft_planes) * fft_smem_bytes <= 40 * 1024 && (long long)N * C >= 2LL * num_sms * 2 * fft_planes) fft_planes *= 2;
+    // a 128^2 plane takes 133 KB of shared memory: one CTA per SM, so it gets 1024 threads (8 warps per SM could not hide the
+    // shared-memory latency of the radix-2 stages between their block barriers); 64^2: two CTAs of 512
+    const int fft_threads = R >= 128 ? 1024 : (R >= 64 ? 512 : 256);
     float* cw_kx = (float*)(((uintptr_t)extra + SHU_PACKED_BYTES + 255) & ~(uintptr_t)255);   // fast64 only (workspace sized for it)
     if (fast64) {
         if (int e = launch_shu_rfft2_r64(x, spec1, cw, cw_kx, N, C, stream)) return e;
     } else if (R <= 128) {
-        if (fft_planes > 1) shu_rfft2_kernel<true><<<ceil_div(N * C, fft_planes), 256, fft_planes * fft_smem_bytes, stream>>>(x, spec1, N * C, C, R, log2R, fft_planes);
-        else shu_rfft2_kernel<false><<<N * C, 256, fft_smem_bytes, stream>>>(x, spec1, N * C, C, R, log2R, 1);
+        if (fft_planes > 1) shu_rfft2_kernel<true><<<ceil_div(N * C, fft_planes), fft_threads, fft_planes * fft_smem_bytes, stream>>>(x, spec1, N * C, C, R, log2R, fft_planes);
+        else shu_rfft2_kernel<false><<<N * C, fft_threads, fft_smem_bytes, stream>>>(x, spec1, N * C, C, R, log2R, 1);
         SHGAN_LAUNCH_CHECK();
     } else {
         const size_t sm_rows = ((size_t)BIG_RP * R + R / 2) * sizeof(float2), sm_cols = ((size_t)R * BIG_CB + R / 2) * sizeof(float2);
@@ -474,8 +477,8 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
         int small_bands = 0;
         while (small_bands < num_bands && (lowest_res << small_bands) <= 128) ++small_bands;
         dim3 igrid(ceil_div(N * C, fft_planes), small_bands);
-        if (fft_planes > 1) shu_irfft2_kernel<true><<<igrid, 256, fft_planes * fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, fft_planes);
-        else shu_irfft2_kernel<false><<<igrid, 256, fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, 1);
+        if (fft_planes > 1) shu_irfft2_kernel<true><<<igrid, fft_threads, fft_planes * fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, fft_planes);
+        else shu_irfft2_kernel<false><<<igrid, fft_threads, fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, 1);
         SHGAN_LAUNCH_CHECK();
     }
     for (int k = 0; k < num_bands; ++k) {
