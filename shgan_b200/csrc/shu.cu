@@ -185,13 +185,15 @@ shu_mix_kernel(const float* __restrict__ spec1, const float* __restrict__ conv0_
 // grid (ceil(N*C / P), num_bands), P planes per CTA; dynamic smem sized for the largest band: colbuf [r][P][rh] + rowbuf [P][r/2][r] + tw [R/2]
 template <bool MULTI>
 __global__ void __launch_bounds__(1024)
-shu_irfft2_kernel(const float* __restrict__ spec2, const float* __restrict__ gauss, ShuBands bands, int NC, int C, int R, int log2R, int P_) {
+shu_irfft2_kernel(const float* __restrict__ spec2, const float* __restrict__ gauss, ShuBands bands, int NC, int C, int R, int log2R, int P_,
+                  int skip_upto) {
     extern __shared__ float2 sm[];
     const int P = MULTI ? P_ : 1;
     const int band = blockIdx.y;
     const int log2r = bands.lowest_log2 + band;
     const int r = 1 << log2r, rh = r / 2 + 1, Rh = R / 2 + 1, rc = r * rh, rr = (r / 2) * r;
     if (r > 128) return;      // large bands run as a column pass + a row pass through global memory
+    if (r <= skip_upto) return;   // bands of at most 32 x 32 run in shu_small.cu (one thread per transform)
     float2* colbuf = sm;
     float2* rowbuf = colbuf + P * rc;
     float2* tw = rowbuf + P * rr;
@@ -444,6 +446,8 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     float* cw_kx = (float*)(((uintptr_t)extra + SHU_PACKED_BYTES + 255) & ~(uintptr_t)255);   // fast64 only (workspace sized for it)
     if (fast64) {
         if (int e = launch_shu_rfft2_r64(x, spec1, cw, cw_kx, N, C, stream)) return e;
+    } else if (R <= 32 && aligned) {
+        if (int e = launch_shu_rfft2_small(x, spec1, N, C, R, stream)) return e;      // one thread per 4 ... 32-point transform
     } else if (R <= 128) {
         if (fft_planes > 1) shu_rfft2_kernel<true><<<ceil_div(N * C, fft_planes), fft_threads, fft_planes * fft_smem_bytes, stream>>>(x, spec1, N * C, C, R, log2R, fft_planes);
         else shu_rfft2_kernel<false><<<N * C, fft_threads, fft_smem_bytes, stream>>>(x, spec1, N * C, C, R, log2R, 1);
@@ -473,12 +477,22 @@ extern "C" int shgan_shu_fwd(const float* x, const float* conv0_w, const float* 
     }
 
     if (fast64) return launch_shu_irfft2_r64(spec2, gauss, bands, N, C, stream);
-    if (lowest_res <= 128) {
+    // bands of at most 32 x 32: one thread per transform (shu_small.cu), one launch per band
+    int skip_upto = 0;
+    if (aligned) {
+        for (int k = 0; k < num_bands; ++k) {
+            const int r = lowest_res << k;
+            if (r > 32) break;
+            if (int e = launch_shu_irfft2_small(spec2, gauss + bands.gauss_off[k], bands.out[k], N, C, R, r, stream)) return e;
+            skip_upto = r;
+        }
+    }
+    if (lowest_res <= 128 && (lowest_res << (num_bands - 1)) > skip_upto) {
         int small_bands = 0;
         while (small_bands < num_bands && (lowest_res << small_bands) <= 128) ++small_bands;
         dim3 igrid(ceil_div(N * C, fft_planes), small_bands);
-        if (fft_planes > 1) shu_irfft2_kernel<true><<<igrid, fft_threads, fft_planes * fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, fft_planes);
-        else shu_irfft2_kernel<false><<<igrid, fft_threads, fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, 1);
+        if (fft_planes > 1) shu_irfft2_kernel<true><<<igrid, fft_threads, fft_planes * fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, fft_planes, skip_upto);
+        else shu_irfft2_kernel<false><<<igrid, fft_threads, fft_smem_bytes, stream>>>(spec2, gauss, bands, N * C, C, R, log2R, 1, skip_upto);
         SHGAN_LAUNCH_CHECK();
     }
     for (int k = 0; k < num_bands; ++k) {

@@ -27,4 +27,9 @@ int launch_shu_mix_tc(const float* spec1, const void* packed, const float* conv0
 int launch_shu_rfft2_r64(const float* x, float* spec1, const float* cw, float* cw_kxmajor, int N, int C, cudaStream_t stream);
 int launch_shu_irfft2_r64(const float* spec2, const float* gauss, const ShuBands& bands, int N, int C, cudaStream_t stream);
 
+// transforms of 4 ... 32 points with one thread per transform (shu_small.cu): the forward pass for input_res <= 32 and the
+// inverse of one band of r <= 32 (spectra in the generic row-major layout of shu.cu; planes and rows 16-byte aligned)
+int launch_shu_rfft2_small(const float* x, float* spec1, int N, int C, int R, cudaStream_t stream);
+int launch_shu_irfft2_small(const float* spec2, const float* gm, float* out, int N, int C, int R, int r, cudaStream_t stream);
+
 }  // namespace shgan

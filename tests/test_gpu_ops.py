@@ -336,10 +336,11 @@ def test_shu_golden(golden):
         assert relerr(yb[r].cpu().numpy(), ref[r]) <= 2e-5
 
 
-@pytest.mark.parametrize('n_in', [256, 512, 4, 8])
+@pytest.mark.parametrize('n_in', [256, 512, 4, 8, 32])
 def test_shu_large_and_small_input_res_vs_oracle(n_in):
     """BASELINE.json config C5 sweeps the unit over input_res 4..512: sizes above 128 run their transforms as row / column
-    passes through global memory; checked against the oracle (numpy pocketfft)."""
+    passes through global memory, sizes up to 32 (and every band of at most 32 x 32) as one register-resident transform per thread
+    (shu_small.cu); checked against the oracle (numpy pocketfft)."""
     from shgan_b200.model_zoo.shgan import SHU
     sd = {k: v for k, v in O.synthetic_state_dict(256, seed=7).items() if k.startswith('encoder.shu')}
     shu = SHU(32, 32, dfilter_freedom=[2, 3], dfilter_type='piecewise_linear', input_res=n_in, lowest_res=4)
