@@ -209,7 +209,7 @@ def reference_gpu_run(cfg, dev, x_d, z_d, steps=5, warmup=3):
 
 
 # ------------------------------------------------------------------------------------------------ SHU sweep (c5)
-def shu_sweep(dev, peaks, resolutions=(4, 8, 16, 32, 64, 128, 256, 512), iters=7):
+def shu_sweep(dev, peaks, resolutions=(4, 8, 16, 32, 64, 128, 256, 512), iters=11):
     import numpy as np
     import torch
     from shgan_b200 import kernels as K, packing as P
@@ -237,6 +237,9 @@ def shu_sweep(dev, peaks, resolutions=(4, 8, 16, 32, 64, 128, 256, 512), iters=7
             def run():
                 K.shu_fwd(x, conv0_w, conv0_b, df1_w, cw, gauss, outs, lowest, workspace=ws, packed=packed)
             for _ in range(3):
+                run()
+            for _ in range(3):                               # and through the flush pattern of the timed loop (fresh pages, TLB, clocks)
+                flush.zero_()
                 run()
         except RuntimeError as ex:
             rows.append(dict(input_res=r, batch=n, unsupported=str(ex)[:120]))
