@@ -695,7 +695,8 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
     // general kernel; fp32 input + full epilogue (synthesis up path) 1.33 ms two-phase vs 1.05 ms register kernel
     const bool identity_epi = !epi.dcoef && epi.wgain == 1.f && !epi.noise && !epi.bias && !epi.act && epi.act_gain == 1.f && !epi.skip_hi &&
                               !epi.next_scale && !epi.out_f32 && epi.out_hi && epi.out_lo;
-    if (rank1_hint && identity_epi && !in_f32 && C % 32 == 0 && !force_two_phase) {
+    const bool planes_aligned = (((uintptr_t)in_hi | (uintptr_t)in_lo | (uintptr_t)epi.out_hi | (uintptr_t)epi.out_lo) & 15) == 0;   // 128-bit cp.async / stores
+    if (rank1_hint && identity_epi && !in_f32 && C % 32 == 0 && planes_aligned && !force_two_phase) {
         // the blur in front of the stride-2 convolutions (planes -> planes): row-walking kernel, no block barriers
         const int xblocks = ceil_div(OW, FW_PX), segs = ceil_div(OH, FW_SEG), cblocks = C / 32;
         const long long items = (long long)xblocks * segs * cblocks * N;
