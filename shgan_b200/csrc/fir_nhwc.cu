@@ -539,7 +539,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 __global__ void __launch_bounds__(256, 2)
 fir4x4_walk_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, const float* __restrict__ f, float gain,
                    int N, int C, int IH, int IW, int OH, int OW, int pad_x0, int pad_y0, __half* __restrict__ out_hi,
-                   __half* __restrict__ out_lo, int parity_split, int xblocks, int segs, int cblocks, int items) {
+                   __half* __restrict__ out_lo, int parity_split, int xblocks, int segs, int cblocks, int items, int seg_rows) {
     extern __shared__ __align__(16) uint8_t fw_smem[];
     __shared__ float s_f[FIR_T * FIR_T];
     if (threadIdx.x < FIR_T * FIR_T) s_f[threadIdx.x] = f[threadIdx.x];
@@ -560,7 +560,7 @@ fir4x4_walk_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ 
     const int c0 = cb * 32 + cg * 8;
     const int x = xb * FW_PX + xl;                         // my output column
     const int ix0 = xb * FW_PX - pad_x0;                   // input column of pixel 0 of the row buffer
-    const int oy0 = seg * FW_SEG, oy1 = min(OH, oy0 + FW_SEG);
+    const int oy0 = seg * seg_rows, oy1 = min(OH, oy0 + seg_rows);
     const int PH = (OH + 1) / 2, PW = (OW + 1) / 2;
     const size_t in_n = (size_t)n * IH * IW;
     uint8_t* wbase = fw_smem + warp * FW_WARP_BYTES;
@@ -698,12 +698,14 @@ extern "C" int shgan_fir_nhwc(const float* in_f32, const void* in_hi, const void
     const bool planes_aligned = (((uintptr_t)in_hi | (uintptr_t)in_lo | (uintptr_t)epi.out_hi | (uintptr_t)epi.out_lo) & 15) == 0;   // 128-bit cp.async / stores
     if (rank1_hint && identity_epi && !in_f32 && C % 32 == 0 && planes_aligned && !force_two_phase) {
         // the blur in front of the stride-2 convolutions (planes -> planes): row-walking kernel, no block barriers
-        const int xblocks = ceil_div(OW, FW_PX), segs = ceil_div(OH, FW_SEG), cblocks = C / 32;
+        // rows per work item: 32 on the large layers (3 halo rows per 32), 8 where the layer would otherwise not fill the GPU
+        const int seg_rows = (long long)ceil_div(OW, FW_PX) * ceil_div(OH, FW_SEG) * (C / 32) * N >= 16LL * 148 ? FW_SEG : 8;
+        const int xblocks = ceil_div(OW, FW_PX), segs = ceil_div(OH, seg_rows), cblocks = C / 32;
         const long long items = (long long)xblocks * segs * cblocks * N;
         SHGAN_CHECK(items <= INT32_MAX, "too many work items");
         fir4x4_walk_kernel<<<(unsigned)ceil_div64(items, 8), 256, FW_SMEM_BYTES, (cudaStream_t)stream>>>(
             (const __half*)in_hi, (const __half*)in_lo, f, gain, N, C, IH, IW, OH, OW, pad_x0, pad_y0, epi.out_hi, epi.out_lo, parity_split,
-            xblocks, segs, cblocks, (int)items);
+            xblocks, segs, cblocks, (int)items, seg_rows);
         SHGAN_LAUNCH_CHECK();
         return 0;
     }

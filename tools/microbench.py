@@ -27,7 +27,7 @@ if 'dense' in which:
         print(f'dense B{B} I{I} O{O}: {us:8.1f} us   weights {w.numel()*4/1e6:.1f} MB -> {w.numel()*4/us/1e3:.0f} GB/s')
 if 'fir' in which:
     f = P.setup_filter([1, 3, 3, 1]).to(dev)
-    for (N, H, C) in [(16, 512, 64), (16, 256, 128), (16, 64, 512)]:
+    for (N, H, C) in [(16, 512, 64), (16, 256, 128), (16, 64, 512), (16, 32, 512), (16, 16, 512), (16, 8, 512)]:
         src = K.Planes.empty(N, H, H, C, dev); src.hi.normal_(); src.lo.normal_(0, 1e-3)
         ph = (H + 2) // 2
         par = K.Planes.empty(4 * N, ph, ph, C, dev)
