@@ -8,8 +8,8 @@
 //  * upfirdn2d_sep4_kernel -- up == down == 1 with a 4x4 filter that is an outer product (the reference's
 //    setup_filter([1,3,3,1]) is; decided on the device, no host sync): the blur passes that carry all the
 //    traffic.  A warp owns 128 output columns of one (n,c) plane and walks down a segment of 64 rows: each
-//    input row is read ONCE with fully coalesced 128-byte loads (the next row is requested before the current
-//    one is consumed), passed through a per-warp shared-memory row so that a lane gets the 7 inputs of its 4
+//    input row is read ONCE, requested seven rows ahead by fully coalesced 4-byte cp.async copies straight into a
+//    per-warp shared-memory ring that doubles as the staged row, so that a lane gets the 7 inputs of its 4
 //    outputs as two 128-bit reads, filtered horizontally (16 FMA) and vertically over a 4-row ring in
 //    registers (16 FMA), and stored as one 128-bit vector: 8 FMA per output instead of 16, no block barrier.
 //  * upfirdn2d_tile_kernel<FH,FW,DOWN>  -- up == 1 with any other 4x4 filter, and the blur+decimate
@@ -55,11 +55,17 @@ __device__ __forceinline__ bool uf_factorise4(const float* __restrict__ f, int f
 constexpr int US_SEG = 64;        // output rows per work item
 constexpr int US_COLS = 128;      // output columns per work item (4 per lane)
 constexpr int US_ROWBUF = 136;    // floats per staged input row: 128 + 3 halo, padded to a multiple of 4
+constexpr int US_STAGES = 8;      // input rows in flight per warp (cp.async ring; the ring IS the staged row: fp32 in, fp32 out)
+constexpr int US_SMEM_BYTES = 8 * US_STAGES * US_ROWBUF * 4;      // 8 warps
+
+__device__ __forceinline__ void us_cp_async4(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
 
 __global__ void __launch_bounds__(256)
 upfirdn2d_sep4_kernel(const float* __restrict__ x, const float* __restrict__ f, float* __restrict__ y, int H, int W, int OH, int OW,
                       int padx0, int pady0, int flip, float gain, int xblocks, int segs, int items) {
-    __shared__ __align__(16) float rowbuf[8][2][US_ROWBUF];
+    extern __shared__ __align__(16) float us_ring[];       // [8 warps][US_STAGES][US_ROWBUF]
     float u[4], v[4];
     const bool sep = uf_factorise4(f, flip, gain, u, v);   // warp-uniform (same filter for every thread)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,31 +79,36 @@ upfirdn2d_sep4_kernel(const float* __restrict__ x, const float* __restrict__ f, 
     float* yp = y + (size_t)plane * OH * OW;
     const int oy0 = seg * US_SEG, oy1 = min(OH, oy0 + US_SEG);
     const int ox = xb * US_COLS + lane * 4;                 // my first output column
-    const int ixb = xb * US_COLS - padx0;                   // input column of rowbuf[0]
-    // coalesced loads of input row iy: columns ixb + k*32 + lane (k < 4) and the 3 halo columns ixb + 128 + lane (lane < 3)
-    auto load_row = [&](int iy, float (&r)[5]) {
+    const int ixb = xb * US_COLS - padx0;                   // input column of ring[.][0]
+    float* ring = us_ring + warp * (US_STAGES * US_ROWBUF);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    // one input row -> ring stage, straight from global memory with fully coalesced 4-byte copies (rows of odd widths are not
+    // 16-byte aligned), zero-filled outside the image: columns ixb + k*32 + lane (k < 4) and the 3 halo columns (lane < 3)
+    auto request_row = [&](int iy, int stage) {
         const bool rv = iy >= 0 && iy < H;
         const float* rp = xp + (size_t)(rv ? iy : 0) * W;
+        const uint32_t d = ring_s + (uint32_t)(stage * US_ROWBUF) * 4u;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
+        for (int k = 0; k < 4; ++k) {
             const int ix = ixb + k * 32 + lane;
-            r[k] = (rv && ix >= 0 && ix < W && (k < 4 || lane < 3)) ? __ldg(rp + ix) : 0.f;
+            const bool ok = rv && ix >= 0 && ix < W;
+            us_cp_async4(d + (uint32_t)(k * 32 + lane) * 4u, rp + (ok ? ix : 0), ok);
         }
+        if (lane < 3) {
+            const int ix = ixb + 128 + lane;
+            const bool ok = rv && ix >= 0 && ix < W;
+            us_cp_async4(d + (uint32_t)(128 + lane) * 4u, rp + (ok ? ix : 0), ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // horizontal 4-tap pass of the staged row: my 4 outputs read rowbuf[lane*4 .. lane*4+6]
-    auto hpass = [&](const float (&r)[5], int b) -> float4 {
-        float* rb = rowbuf[warp][b];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) rb[k * 32 + lane] = r[k];
-        if (lane < 3) rb[128 + lane] = r[4];
+    // row r of the walk (r = 0 is input row oy0 - pady0) lives in stage r % US_STAGES; rows up to r + US_STAGES - 2 have been
+    // requested when row r is consumed.  The warp barrier makes every lane's copies of row r visible to the others and proves
+    // that all lanes are done with row r - 1, whose stage the next request overwrites.
+    auto acquire = [&](int r, int iy_base) -> const float* {
+        asm volatile("cp.async.wait_group %0;" ::"n"(US_STAGES - 2) : "memory");
         __syncwarp();
-        const float4 a = *reinterpret_cast<const float4*>(rb + lane * 4), c = *reinterpret_cast<const float4*>(rb + lane * 4 + 4);
-        float4 h;
-        h.x = fmaf(v[3], a.w, fmaf(v[2], a.z, fmaf(v[1], a.y, v[0] * a.x)));
-        h.y = fmaf(v[3], c.x, fmaf(v[2], a.w, fmaf(v[1], a.z, v[0] * a.y)));
-        h.z = fmaf(v[3], c.y, fmaf(v[2], c.x, fmaf(v[1], a.w, v[0] * a.z)));
-        h.w = fmaf(v[3], c.z, fmaf(v[2], c.y, fmaf(v[1], c.x, v[0] * a.w)));
-        return h;
+        request_row(iy_base + r + US_STAGES - 1, (r + US_STAGES - 1) % US_STAGES);
+        return ring + (r % US_STAGES) * US_ROWBUF + lane * 4;        // my 7 inputs: [0..6]
     };
     const bool vec_ok = (OW & 3) == 0 && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
     auto store4 = [&](int oy, const float4& o) {
@@ -112,35 +123,24 @@ upfirdn2d_sep4_kernel(const float* __restrict__ x, const float* __restrict__ f, 
             if (ox + 3 < OW) dst[3] = o.w;
         }
     };
+    const int iy0 = oy0 - pady0;
+#pragma unroll
+    for (int r = 0; r < US_STAGES - 1; ++r) request_row(iy0 + r, r);
     if (!sep) {
-        // any other 4x4 filter: same walk, the ring holds the last four RAW rows (7 inputs each) and every output takes its 16 taps
+        // any other 4x4 filter: same walk, the ring of registers holds the last four RAW rows (7 inputs each), 16 taps per output
         float a[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) a[i] = __ldg(f + (flip ? i : 15 - i)) * gain;
-        auto stage = [&](const float (&r)[5], int bb, float (&w)[7]) {
-            float* rb = rowbuf[warp][bb];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) rb[k * 32 + lane] = r[k];
-            if (lane < 3) rb[128 + lane] = r[4];
-            __syncwarp();
-            const float4 p = *reinterpret_cast<const float4*>(rb + lane * 4), q = *reinterpret_cast<const float4*>(rb + lane * 4 + 4);
+        auto fetch = [&](int r, float (&w)[7]) {
+            const float* s = acquire(r, iy0);
+            const float4 p = *reinterpret_cast<const float4*>(s), q = *reinterpret_cast<const float4*>(s + 4);
             w[0] = p.x; w[1] = p.y; w[2] = p.z; w[3] = p.w; w[4] = q.x; w[5] = q.y; w[6] = q.z;
         };
-        float r0[5], r1[5], w0[7], w1[7], w2[7], w3[7];
-        int iy = oy0 - pady0;
-        load_row(iy, r0);
-        load_row(iy + 1, r1);
-        stage(r0, 0, w0);
-        load_row(iy + 2, r0);
-        stage(r1, 1, w1);
-        load_row(iy + 3, r1);
-        stage(r0, 0, w2);
-        iy += 3;
-        int b = 1;
-        for (int oy = oy0; oy < oy1; ++oy) {
-            load_row(iy + 1, r0);
-            stage(r1, b, w3);
-            b ^= 1;
+        float w0[7], w1[7], w2[7], w3[7];
+        fetch(0, w0); fetch(1, w1); fetch(2, w2);
+        int r = 3;
+        for (int oy = oy0; oy < oy1; ++oy, ++r) {
+            fetch(r, w3);
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -157,43 +157,35 @@ upfirdn2d_sep4_kernel(const float* __restrict__ x, const float* __restrict__ f, 
             store4(oy, make_float4(o[0], o[1], o[2], o[3]));
 #pragma unroll
             for (int k = 0; k < 7; ++k) { w0[k] = w1[k]; w1[k] = w2[k]; w2[k] = w3[k]; }
-#pragma unroll
-            for (int k = 0; k < 5; ++k) r1[k] = r0[k];
-            ++iy;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         return;
     }
-    // output row oy = sum_k u[k] * hrow(iy = oy - pady0 + k): prime the ring with the first three input rows of the segment
-    float r0[5], r1[5];
-    float4 h0, h1, h2, h3;
-    int iy = oy0 - pady0;
-    load_row(iy, r0);
-    load_row(iy + 1, r1);
-    h0 = hpass(r0, 0);
-    load_row(iy + 2, r0);
-    h1 = hpass(r1, 1);
-    load_row(iy + 3, r1);
-    h2 = hpass(r0, 0);
-    iy += 3;                                                // r1 holds row iy
-    int b = 1;
-    for (int oy = oy0; oy < oy1; ++oy) {
-        // r1 = input row oy - pady0 + 3 (already requested); request the row after it before consuming
-        load_row(iy + 1, r0);
-        h3 = hpass(r1, b);
-        b ^= 1;
-        {
-            float4 o;
-            o.x = fmaf(u[3], h3.x, fmaf(u[2], h2.x, fmaf(u[1], h1.x, u[0] * h0.x)));
-            o.y = fmaf(u[3], h3.y, fmaf(u[2], h2.y, fmaf(u[1], h1.y, u[0] * h0.y)));
-            o.z = fmaf(u[3], h3.z, fmaf(u[2], h2.z, fmaf(u[1], h1.z, u[0] * h0.z)));
-            o.w = fmaf(u[3], h3.w, fmaf(u[2], h2.w, fmaf(u[1], h1.w, u[0] * h0.w)));
-            store4(oy, o);
-        }
+    // separable: horizontal 4-tap pass of each row (my 4 outputs read ring[lane*4 .. lane*4+6]), vertical pass over a ring of the
+    // last four horizontal rows in registers: output row oy = sum_k u[k] * hrow(oy - pady0 + k)
+    auto hpass = [&](int r) -> float4 {
+        const float* s = acquire(r, iy0);
+        const float4 a = *reinterpret_cast<const float4*>(s), c = *reinterpret_cast<const float4*>(s + 4);
+        float4 h;
+        h.x = fmaf(v[3], a.w, fmaf(v[2], a.z, fmaf(v[1], a.y, v[0] * a.x)));
+        h.y = fmaf(v[3], c.x, fmaf(v[2], a.w, fmaf(v[1], a.z, v[0] * a.y)));
+        h.z = fmaf(v[3], c.y, fmaf(v[2], c.x, fmaf(v[1], a.w, v[0] * a.z)));
+        h.w = fmaf(v[3], c.z, fmaf(v[2], c.y, fmaf(v[1], c.x, v[0] * a.w)));
+        return h;
+    };
+    float4 h0 = hpass(0), h1 = hpass(1), h2 = hpass(2), h3;
+    int r = 3;
+    for (int oy = oy0; oy < oy1; ++oy, ++r) {
+        h3 = hpass(r);
+        float4 o;
+        o.x = fmaf(u[3], h3.x, fmaf(u[2], h2.x, fmaf(u[1], h1.x, u[0] * h0.x)));
+        o.y = fmaf(u[3], h3.y, fmaf(u[2], h2.y, fmaf(u[1], h1.y, u[0] * h0.y)));
+        o.z = fmaf(u[3], h3.z, fmaf(u[2], h2.z, fmaf(u[1], h1.z, u[0] * h0.z)));
+        o.w = fmaf(u[3], h3.w, fmaf(u[2], h2.w, fmaf(u[1], h1.w, u[0] * h0.w)));
+        store4(oy, o);
         h0 = h1; h1 = h2; h2 = h3;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) r1[k] = r0[k];
-        ++iy;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <int FH, int FW, int DOWN>
@@ -385,7 +377,7 @@ extern "C" int shgan_upfirdn2d_fwd(const float* x, const float* f, float* y, int
         const int xblocks = ceil_div(OW, US_COLS), segs = ceil_div(OH, US_SEG);
         const long long items = (long long)xblocks * segs * N * C;
         SHGAN_CHECK(items <= INT32_MAX, "grid too large");
-        upfirdn2d_sep4_kernel<<<(unsigned)ceil_div64(items, 8), 256, 0, stream>>>(x, f, y, H, W, OH, OW, padx0, pady0, flip, gain, xblocks,
+        upfirdn2d_sep4_kernel<<<(unsigned)ceil_div64(items, 8), 256, US_SMEM_BYTES, stream>>>(x, f, y, H, W, OH, OW, padx0, pady0, flip, gain, xblocks,
                                                                                   segs, (int)items);
         SHGAN_LAUNCH_CHECK();
         return 0;
