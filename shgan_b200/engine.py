@@ -491,6 +491,11 @@ class GeneratorEngine:
         self._ensure()
         masked = isinstance(x, (tuple, list))      # (real, mask): see encoder()
         xin = list(x) if masked else [x]
+        if xin[0].shape[0] == 0:
+            # empty batch: empty results, like the reference's PyTorch ops (the kernels take no null / zero-size tensors)
+            r = xin[0].shape[-1]
+            img = torch.empty((0, 3, r, r), dtype=torch.float32, device=xin[0].device)
+            return (img, torch.empty((0, 3, r, r), dtype=torch.uint8, device=xin[0].device)) if composite else img
         if not (self.graphs and xin[0].is_cuda):
             return self._forward_eager(x, z, noise_mode, composite)
         key = (tuple(tuple(t.shape) for t in xin), tuple(z.shape), noise_mode, composite, self.passes, self.impl, self.fuse_up2)
@@ -626,6 +631,8 @@ class DiscriminatorEngine:
     def forward(self, img):
         img = img.contiguous().float()
         n = img.shape[0]
+        if n == 0:
+            return torch.empty((0, 1), dtype=torch.float32, device=img.device)      # empty batch: empty logits
         g = math.sqrt(0.5)
         conv = lambda srcs, L, taps, oh, ow, epi: K.conv_igemm(srcs, L['w_hi'], L['w_lo'], taps, oh, ow, epi=epi,
                                                                passes=self.passes, impl=self.impl)

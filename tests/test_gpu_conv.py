@@ -240,6 +240,22 @@ def test_generator_tc_vs_simt_batch_and_random_noise():
     assert np.abs(one[0] - three[0]).max() <= 1e-3 * max(1.0, np.abs(three).max())
 
 
+def test_generator_tc_ragged_and_empty_batch():
+    """The last batch of an eval run is ragged (shgan_default.py:269-274 feeds whatever the sampler returns): batch 1 against the
+    oracle, and an empty batch returns an empty image like the reference's PyTorch ops do."""
+    sd = O.synthetic_state_dict(128, seed=11, ch_base=8192, ch_max=64)
+    G = H.build_generator(128, sd, 8192, 64, device=DEV)
+    x, z = O.synthetic_inputs(3, 128, seed=11)
+    for n in (1, 3):
+        img = G(t(x[:n]), t(z[:n]), None, noise_mode='const').cpu().numpy()
+        ref = O.generator(sd, x[:n], z[:n], 128)
+        assert img.shape == ref.shape and np.abs(img - ref).max() <= 1e-3
+    img0 = G(t(x[:0]), t(z[:0]), None, noise_mode='const')
+    assert tuple(img0.shape) == (0, 3, 128, 128)
+    img0, comp0 = G.forward_composite(t(x[:0]), t(z[:0]), noise_mode='random')
+    assert tuple(img0.shape) == (0, 3, 128, 128) and tuple(comp0.shape) == (0, 3, 128, 128) and comp0.dtype == torch.uint8
+
+
 def test_generator_tc_state_dict_reload_and_deepcopy():
     import copy
     sd1 = O.synthetic_state_dict(128, seed=1, ch_base=8192, ch_max=64)
