@@ -90,8 +90,11 @@ fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ mask, floa
 // the whole kernel and the activation gain is folded into them (lrelu(v) * g == lrelu(v * g) for g > 0).  ncu on the generic
 // kernel above (profiles/r2_fromrgb_ncu.md): 300 issued instructions per 8 outputs -- every iteration re-read its 4x8 weights
 // from shared memory (93 % L1 pipe, short-scoreboard stalls) and ran the MAX_CI = 8 loop with half of it predicated off.
+#ifndef FRGB_MINB
+#define FRGB_MINB 4
+#endif
 template <int CI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FRGB_MINB)
 fromrgb_fast_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ x_out, const float* __restrict__ w,
                     const float* __restrict__ bias, float wgain, float act_alpha, float act_gain, float act_clamp,
                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int Co, int HW) {
@@ -110,33 +113,47 @@ fromrgb_fast_kernel(const float* __restrict__ x, const float* __restrict__ mask,
     }
     const float clampv = act_clamp > 0.f ? act_clamp : __int_as_float(0x7f800000);
     unsigned n = pix / (unsigned)HW, p = pix - n * (unsigned)HW;
-    for (; pix < total_pix; pix += pstride) {
-        float xin[CI];
+    // the layer input of pixel (n, p): [mask - 0.5, real * mask] when the input preparation is fused, the NCHW input otherwise
+    auto load_in = [&](unsigned nn, unsigned pp, float (&xin)[CI]) {
         if (mask) {
-            const float m = __ldg(mask + (size_t)n * HW + p);
+            const float m = __ldg(mask + (size_t)nn * HW + pp);
             xin[0] = m - 0.5f;
 #pragma unroll
-            for (int i = 1; i < CI; ++i) xin[i] = __ldg(x + ((size_t)n * (CI - 1) + (i - 1)) * HW + p) * m;
-            if (cg == 0) {
-#pragma unroll
-                for (int i = 0; i < CI; ++i) x_out[((size_t)n * CI + i) * HW + p] = xin[i];
-            }
+            for (int i = 1; i < CI; ++i) xin[i] = __ldg(x + ((size_t)nn * (CI - 1) + (i - 1)) * HW + pp) * m;
         } else {
 #pragma unroll
-            for (int i = 0; i < CI; ++i) xin[i] = __ldg(x + ((size_t)n * CI + i) * HW + p);
+            for (int i = 0; i < CI; ++i) xin[i] = __ldg(x + ((size_t)nn * CI + i) * HW + pp);
+        }
+    };
+    // software pipeline: the next pixel's inputs are requested before the current pixel is computed and stored.  One dependent
+    // DRAM round trip per iteration held this kernel at 2.7 TB/s of stores (394 us); a plain fill kernel writes 7.4 TB/s on this
+    // GPU (tools/hbm_write_probe.py).  Pairs of pixels per iteration measured slower (375 us: 99 registers, two CTAs per SM).
+    float cur[CI], nxt[CI];
+    if (pix < total_pix) load_in(n, p, cur);
+    while (pix < total_pix) {
+        const unsigned pix_n = pix + pstride;               // (pixel indices < 2^31 and pstride < 2^28: no wrap-around)
+        unsigned n_n = n, p_n = p + pstride;
+        while (p_n >= (unsigned)HW) { p_n -= (unsigned)HW; ++n_n; }
+#pragma unroll
+        for (int i = 0; i < CI; ++i) nxt[i] = 0.f;
+        if (pix_n < total_pix) load_in(n_n, p_n, nxt);
+        if (mask && cg == 0) {
+#pragma unroll
+            for (int i = 0; i < CI; ++i) x_out[((size_t)n * CI + i) * HW + p] = cur[i];
         }
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float a = br[j];
 #pragma unroll
-            for (int i = 0; i < CI; ++i) a = fmaf(xin[i], wr[i][j], a);
+            for (int i = 0; i < CI; ++i) a = fmaf(cur[i], wr[i][j], a);
             a = fmaxf(a, a * act_alpha);                                   // lrelu (0 <= alpha <= 1), gain already applied
             v[j] = fminf(fmaxf(a, -clampv), clampv);
         }
         store_planes8(out_hi, out_lo, (long long)((size_t)pix * Co + cg * 8), v);
-        p += pstride;
-        while (p >= (unsigned)HW) { p -= (unsigned)HW; ++n; }
+#pragma unroll
+        for (int i = 0; i < CI; ++i) cur[i] = nxt[i];
+        pix = pix_n; n = n_n; p = p_n;
     }
 }
 
