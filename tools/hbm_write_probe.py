@@ -1,3 +1,5 @@
+"""What pure streams reach on this GPU (development aid): memset / fill / copy / reduction over 1 GiB,
+CUDA events.  Measured on B200: fill 7.45 TB/s, reduction 5.9 TB/s, copy 6.5 TB/s (read + write), byte memset 3.9 TB/s."""
 import torch
 d='cuda'
 a=torch.empty(1<<30, dtype=torch.uint8, device=d); b=torch.empty(1<<30, dtype=torch.uint8, device=d)
